@@ -1,0 +1,272 @@
+/*
+ * pinn_b200.h — C ABI of the B200-native PINN fit-step engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of analysiscenter/pydens that this
+ * repository replaces: the body of the training loop of `Solver.fit`
+ * (reference: pydens/model_torch.py:426-464).  The reference has no FFI layer of its own
+ * (it is pure Python on PyTorch autograd), so every entry point below cites the reference
+ * lines whose work it takes over.  The Python host side (pydens_b200/solver.py) binds this
+ * library with ctypes; see INTEGRATION.md for the binding a pydens maintainer would add.
+ *
+ * Conventions
+ *   - All `float*` / `void*` data pointers are DEVICE pointers owned by the caller
+ *     (PyTorch tensors), borrowed for the duration of the call, 16-byte aligned.
+ *   - All calls are stream-ordered on `stream` (a cudaStream_t passed as void*), perform
+ *     no allocation and no host synchronisation, and are CUDA-graph capturable
+ *     (pinn_plan_create / pinn_plan_destroy excepted: they allocate a small device copy of
+ *     the plan and must not be called during capture).
+ *   - Return value: 0 on success, negative PINN_E_* on failure; pinn_last_error() gives a
+ *     thread-local human readable message.
+ *   - A plan is immutable after creation and may be used from several streams.
+ *
+ * No torch types appear in this interface.
+ */
+#ifndef PINN_B200_H
+#define PINN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINN_ABI_VERSION   3
+
+#define PINN_MAX_LAYERS    16   /* linear layers                                   */
+#define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
+#define PINN_MAX_DIRS       6   /* first-order derivative directions (NF)          */
+#define PINN_MAX_VARS       4   /* scalar V() variables used inside the equation   */
+#define PINN_MAX_PROG     192   /* instructions per expression program             */
+#define PINN_MAX_SLOTS     96   /* scratch slots of an expression program          */
+
+/* error codes */
+#define PINN_OK             0
+#define PINN_E_INVALID     -1   /* malformed spec / argument                       */
+#define PINN_E_UNSUPPORTED -2   /* valid request outside what the kernels cover    */
+#define PINN_E_CUDA        -3   /* CUDA runtime error (message has the detail)     */
+#define PINN_E_ALIGN       -4   /* pointer not 16-byte aligned                     */
+#define PINN_E_WORKSPACE   -5   /* workspace too small                             */
+
+/* activation ids (reference: batchflow Block `activation=` names used by
+ * pydens/model_torch.py:158-168; 'Tanh' README.md:41, 'Sigmoid' model_torch.py:159) */
+#define PINN_ACT_NONE       0
+#define PINN_ACT_TANH       1
+#define PINN_ACT_SIGMOID    2
+#define PINN_ACT_SIN        3
+
+/* expression-program opcodes: a tiny register machine evaluated once per collocation
+ * point.  Programs are produced on the host by tracing the user's `equation` /
+ * `initial_condition` callables (reference: the opaque Python callables invoked at
+ * pydens/model_torch.py:448 and :127) and differentiating them symbolically. */
+enum PinnOp {
+    PINN_OP_CONST = 0,  /* dst = imm                                   */
+    PINN_OP_COORD = 1,  /* dst = x[a]            (column a of the point) */
+    PINN_OP_VAR   = 2,  /* dst = V[a]            (a-th equation variable) */
+    PINN_OP_ADD   = 3,  /* dst = s[a] + s[b]     */
+    PINN_OP_SUB   = 4,
+    PINN_OP_MUL   = 5,
+    PINN_OP_DIV   = 6,
+    PINN_OP_NEG   = 7,  /* dst = -s[a]           */
+    PINN_OP_MULI  = 8,  /* dst = s[a] * imm      */
+    PINN_OP_ADDI  = 9,  /* dst = s[a] + imm      */
+    PINN_OP_SIN   = 10,
+    PINN_OP_COS   = 11,
+    PINN_OP_EXP   = 12,
+    PINN_OP_LOG   = 13,
+    PINN_OP_SQRT  = 14,
+    PINN_OP_TANH  = 15,
+    PINN_OP_POWI  = 16, /* dst = s[a] ** (int)imm */
+    PINN_OP_POW   = 17, /* dst = powf(s[a], s[b]) */
+    PINN_OP_ABS   = 18,
+    PINN_OP_SIGN  = 19,
+    PINN_OP_SIGMOID = 20,
+    PINN_OP_RECIP = 21, /* dst = 1 / s[a]        */
+    PINN_OP_TAN   = 22,
+    PINN_OP_COUNT_
+};
+
+typedef struct PinnInstr {
+    uint8_t op, dst, a, b;
+    float   imm;
+} PinnInstr;
+
+/* sampler column kinds (reference: default `torch.rand` columns model_torch.py:431 and
+ * batchflow NumpySampler 'uniform'/'normal' used at README.md:82, tutorial cell `NS('u', ...)`) */
+#define PINN_COL_UNIFORM    0   /* a + (b - a) * U[0,1)   */
+#define PINN_COL_NORMAL     1   /* a + b * N(0,1)          */
+#define PINN_COL_CONST      2   /* a                       */
+
+typedef struct PinnColumn {
+    int32_t kind;
+    float   a, b;
+} PinnColumn;
+
+/*
+ * Everything that defines one `Solver`: network, ansatz, derivative jet set, residual.
+ *
+ * Network (reference ConvBlockModel.forward model_torch.py:170-172, layouts 'fa…f'):
+ *   n_layers linear layers, widths[0] = ndims + nparams, widths[n_layers] = 1;
+ *   act[l] is the activation applied AFTER linear layer l (0-based); act[n_layers-1] must
+ *   be PINN_ACT_NONE.
+ * Flat parameter buffer (fp32): for layer l the weight matrix [widths[l+1] x widths[l]]
+ *   row-major (== torch nn.Linear.weight) at w_off[l] and the bias at b_off[l]; the scalar
+ *   log_scale (model_torch.py:50) at log_scale_off; equation variables (V token,
+ *   model_torch.py:180-188) at var_off[i].  n_params = number of floats in the buffer,
+ *   rounded up by the caller to a multiple of 4.  The gradient buffer uses the same layout.
+ *
+ * Ansatz (reference TorchModel.anzatc model_torch.py:107-128):
+ *   has_bc: u = N * prod_i g_i(x_i) + bc_value over the first ndims_spatial columns,
+ *           g_i(x) = (x - lo_i)(hi_i - x) / (hi_i - lo_i)^2;
+ *   has_ic: u = (sigmoid((t - t0) / exp(log_scale)) - 0.5) * u + ic(x_spatial),
+ *           t = column ndims-1, t0 = dom_lo[ndims-1], ic given by ic_prog.
+ *
+ * Jet set (what the nested D() calls of the equation need, model_torch.py:174-178):
+ *   nf first-order directions; direction d differentiates along point column dir_col[d];
+ *   the first ns (<= nf) of them additionally carry the second derivative along the same
+ *   column.  Channel order of every jet: [value, d/dx_dir0.., d2/dx_dir0^2 ..].
+ *
+ * Programs: scratch slots 0..C-1 (C = 1 + nf + ns) are preloaded with the jet of u before
+ *   eq_prog runs.  eq_out[0] is the slot of the residual r, eq_out[1+c] the slot of
+ *   dr/d(jet channel c), eq_out[1+C+i] the slot of dr/dV_i.  ic_prog runs before u is
+ *   assembled (it reads only PINN_OP_COORD leaves); ic_out[c] is the slot holding channel c
+ *   of the jet of ic.
+ */
+typedef struct PinnSpec {
+    int32_t  abi_version;
+    int32_t  n_layers;
+    int32_t  widths[PINN_MAX_LAYERS + 1];
+    int32_t  act[PINN_MAX_LAYERS];
+    int32_t  w_off[PINN_MAX_LAYERS];
+    int32_t  b_off[PINN_MAX_LAYERS];
+    int32_t  n_params;
+    int32_t  log_scale_off;
+    int32_t  n_vars;
+    int32_t  var_off[PINN_MAX_VARS];
+
+    int32_t  ndims, nparams;
+    int32_t  has_bc, has_ic;
+    float    bc_value;
+    float    dom_lo[PINN_MAX_DIMS], dom_hi[PINN_MAX_DIMS];
+
+    int32_t  nf, ns;
+    int32_t  dir_col[PINN_MAX_DIRS];
+
+    int32_t   n_eq;
+    PinnInstr eq_prog[PINN_MAX_PROG];
+    int32_t   eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
+    int32_t   n_ic;
+    PinnInstr ic_prog[PINN_MAX_PROG];
+    int32_t   ic_out[1 + 2 * PINN_MAX_DIRS];
+    int32_t   n_slots;          /* scratch slots either program may touch */
+} PinnSpec;
+
+typedef struct PinnPlan PinnPlan;
+
+/* Thread-local message of the last failing call. */
+const char* pinn_last_error(void);
+
+/* ABI version of the loaded library (== PINN_ABI_VERSION of the header it was built from). */
+int pinn_abi_version(void);
+
+/* Validate `spec`, pick the kernel variant for its jet set and widths, upload the device
+ * copy.  Host-side, done once per Solver — the counterpart of Solver.__init__'s model
+ * construction (model_torch.py:312-325); NOT on the hot path. */
+int pinn_plan_create(const PinnSpec* spec, int device, PinnPlan** out);
+int pinn_plan_destroy(PinnPlan* plan);
+
+/* Bytes of device workspace pinn_step / pinn_forward need for up to `n_points` points per
+ * call.  (Cross-CTA partial sums, the grid ticket, and — for networks whose activations do
+ * not fit shared memory — the activation spill area.) */
+size_t pinn_workspace_bytes(const PinnPlan* plan, int64_t n_points);
+
+/* Number of floats of the `grads_and_loss` buffer: n_params (multiple of 4) + 4. */
+int pinn_out_floats(const PinnPlan* plan);
+
+/*
+ * ONE fit step minus the optimizer: replaces model_torch.py:430-460, i.e. sampling (:430-436),
+ * concat (:437), model forward + ansatz (:438), the D()-built residual (:448), MSE (:448) and
+ * loss.backward() (:460).
+ *
+ *   params          [n_params] flat fp32 parameters.
+ *   points          [n_points, ndims+nparams] row-major fp32, or NULL to sample in-kernel.
+ *   cols            (points == NULL) host pointer to ndims+nparams column descriptors; NULL
+ *                   means U[0,1) on every column (reference default, model_torch.py:431).
+ *   seed            Philox key.
+ *   step_counter    device pointer to a uint64 step number (Philox counter word; advanced
+ *                   by pinn_record_loss) or NULL to use `step_value`.
+ *   point_offset    global index of this call's first point (rank shard offset), so that the
+ *                   sampled stream does not depend on how the batch is sharded.
+ *   n_points        points processed by THIS call.
+ *   inv_global_n    1 / (global batch size): the MSE mean of model_torch.py:448 is taken over
+ *                   the global batch, so per-rank outputs simply add up.
+ *   grads_and_loss  [n_params + 4] overwritten: d(loss)/d(params) in params layout, then
+ *                   [n_params] = this call's share of the loss (sum r^2 * inv_global_n).
+ *   residual_out    optional [n_points] per-point residual (debug / parity), or NULL.
+ */
+int pinn_step(const PinnPlan* plan,
+              const float* params,
+              const float* points,
+              const PinnColumn* cols,
+              uint64_t seed,
+              const uint64_t* step_counter,
+              uint64_t step_value,
+              uint64_t point_offset,
+              int64_t n_points,
+              float inv_global_n,
+              float* grads_and_loss,
+              float* residual_out,
+              void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* Forward only: u = ansatz(net(x)) for explicit points — the work of Solver.predict
+ * (model_torch.py:466-487) and of the `_forward` closure handed to constraints (:451-454).
+ * u_out [n_points]. */
+int pinn_forward(const PinnPlan* plan,
+                 const float* params,
+                 const float* points,
+                 int64_t n_points,
+                 float* u_out,
+                 void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Write the points the in-kernel sampler would produce for (seed, step, point_offset ..)
+ * to points_out [n_points, ndims+nparams]: lets tests replay a sampled batch explicitly. */
+int pinn_sample(const PinnPlan* plan,
+                const PinnColumn* cols,
+                uint64_t seed,
+                const uint64_t* step_counter,
+                uint64_t step_value,
+                uint64_t point_offset,
+                int64_t n_points,
+                float* points_out,
+                void* stream);
+
+/* losses_ring[*step_counter % ring_len] = grads_and_loss[n_params]; ++*step_counter.
+ * The device-side replacement for `self.losses.append(loss.detach().cpu().numpy())`
+ * (model_torch.py:464), which forces a host sync every iteration in the reference. */
+int pinn_record_loss(const PinnPlan* plan,
+                     const float* grads_and_loss,
+                     float* losses_ring, int64_t ring_len,
+                     uint64_t* step_counter,
+                     void* stream);
+
+/* Introspection for tests / bench: kernel variant actually selected. */
+typedef struct PinnPlanInfo {
+    int32_t nf, ns, channels;
+    int32_t threads_per_cta;
+    int32_t ctas_per_sm;
+    int32_t activations_in_smem;      /* 1: shared memory, 0: global workspace           */
+    int32_t smem_bytes;
+    int32_t regs_per_thread;
+    int32_t sm_count;
+    int32_t rows_per_point;           /* floats of per-point state kept between fwd/bwd  */
+    int64_t flops_per_point;          /* algorithmic 6*C*M                */
+    int32_t bytes_per_point;          /* algorithmic 4*(ndims+nparams)                   */
+} PinnPlanInfo;
+int pinn_plan_info(const PinnPlan* plan, PinnPlanInfo* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINN_B200_H */

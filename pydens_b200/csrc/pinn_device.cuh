@@ -1,0 +1,850 @@
+// pinn_device.cuh — per-point math of the fused PINN fit step (sm_100a).
+//
+// Everything in this header is written per THREAD: one thread owns one collocation point and
+// walks the whole step for it (MLP forward carrying a Taylor jet, ansatz, residual program,
+// hand-derived reverse sweep).  The functions are `__host__ __device__` so the very same code
+// can be compiled by g++ into the test-only emulation harness (tests/emul/) and checked against
+// the fp64 oracle on a machine without a GPU.  Cross-lane work (the weight-gradient reduction)
+// is isolated in emit_entries().
+//
+// Reference semantics being reproduced (analysiscenter/pydens, pydens/model_torch.py):
+//   forward  :170-172 (MLP via batchflow Block) + anzatc :107-128
+//   D()      :174-178 — nested autograd.grad == the jet channels carried here
+//   loss     :448     — MSE of the residual
+//   backward :460     — the reverse sweep below (SURVEY.md §3.3 has the derivation)
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include "../../include/pinn_b200.h"
+
+#if defined(__CUDACC__)
+#define PINN_HD __host__ __device__ __forceinline__
+#define PINN_D  __device__ __forceinline__
+#else
+#define PINN_HD inline
+#define PINN_D  inline
+#endif
+
+namespace pinn {
+
+// ----------------------------------------------------------------------------------------------
+// Device-side plan (lives in global memory, copied to shared memory by every CTA).
+// ----------------------------------------------------------------------------------------------
+struct DevLayer {
+    int n_in, n_out, act;       // act = activation applied to this layer's output
+    int w_off, b_off;           // offsets in the flat parameter buffer
+    int wt_s;                   // smem float offset of Wt [n_in][n_out_p4]   (forward layout)
+    int w_s;                    // smem float offset of W  [n_out_p4][n_in_p8] (reverse layout)
+    int b_s;                    // smem float offset of bias [n_out_p4]
+    int n_out_p4, n_in_p8;
+    int unit_base;              // first unit index of this layer's output buffer
+    int pad_;
+};
+
+struct alignas(16) DevPlan {
+    int n_layers;
+    int total, ndims, nparams, nsp;     // nsp = number of spatial dims (ndims or ndims-1)
+    int has_bc, has_ic;
+    int nf, ns;
+    int n_params;                       // floats in the flat buffer (multiple of 4)
+    int log_scale_off;
+    int n_vars;
+    int n_eq, n_ic, n_slots;
+    int row_units, row_scr, rows_total; // per-point storage rows
+    int weights_floats;                 // floats of the smem weight area
+    int n_units;
+    float bc;
+    float t0;
+    int dir_col[PINN_MAX_DIRS];
+    int var_off[PINN_MAX_VARS];
+    float lo[PINN_MAX_DIMS], hi[PINN_MAX_DIMS], inv_w2[PINN_MAX_DIMS];
+    int eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
+    int ic_out[1 + 2 * PINN_MAX_DIRS];
+    PinnColumn cols[PINN_MAX_DIMS];     // sampler columns of the current call
+    DevLayer layer[PINN_MAX_LAYERS];
+    PinnInstr eq[PINN_MAX_PROG];
+    PinnInstr ic[PINN_MAX_PROG];
+};
+
+// ----------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) — counter-based RNG for in-kernel collocation sampling.
+// Restated bit-exactly in oracle/philox.py.
+// ----------------------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+PINN_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+PINN_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                              uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n1 = lo1;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        uint32_t n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+PINN_HD float u01_from_bits(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-08f; }  // [0,1)
+
+PINN_HD uint32_t philox_word(const Philox4& p, int i) {
+    return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
+}
+
+// Coordinate k of the point with global index `gidx` at step `step`.
+// Counter = (gidx lo, gidx hi, step lo, (step hi & 0xffff) << 16 | block); key = seed.
+// block 0/1 serve uniform columns 0-3 / 4-7 (one word each); block 2+k serves normal column k.
+PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_t step, uint64_t seed,
+                            const Philox4& blk0, const Philox4& blk1) {
+    if (col.kind == PINN_COL_CONST) return col.a;
+    if (col.kind == PINN_COL_UNIFORM) {
+        uint32_t w = (k < 4) ? philox_word(blk0, k) : philox_word(blk1, k - 4);
+        float u = u01_from_bits(w);
+        return fmaf(col.b - col.a, u, col.a);
+    }
+    // normal: Box-Muller on a dedicated Philox block
+    uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16) | (uint32_t)(2 + k);
+    Philox4 p = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    float u1 = ((float)(p.x >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0,1]
+    float u2 = u01_from_bits(p.y);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float z = rad * cosf(6.283185307179586f * u2);
+    return fmaf(col.b, z, col.a);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Activations.  A hidden unit stores `s` (tanh/sigmoid: the activation value itself; sin: the
+// pre-activation) and everything else is rebuilt from it without another transcendental.
+// ----------------------------------------------------------------------------------------------
+struct ActD { float a, s1, s2, s3; };   // value, sigma', sigma'', sigma'''
+
+PINN_HD float act_store(int act, float z) {
+    switch (act) {
+        case PINN_ACT_TANH:    return tanhf(z);
+        case PINN_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+        default:               return z;           // NONE, SIN keep z
+    }
+}
+
+PINN_HD ActD act_from_stored(int act, float s) {
+    ActD r;
+    switch (act) {
+        case PINN_ACT_TANH: {
+            r.a = s; r.s1 = fmaf(-s, s, 1.0f); r.s2 = -2.0f * s * r.s1;
+            r.s3 = -2.0f * r.s1 * fmaf(-3.0f * s, s, 1.0f);
+        } break;
+        case PINN_ACT_SIGMOID: {
+            r.a = s; r.s1 = s * (1.0f - s); r.s2 = r.s1 * fmaf(-2.0f, s, 1.0f);
+            r.s3 = r.s1 * fmaf(6.0f * s, s - 1.0f, 1.0f);
+        } break;
+        case PINN_ACT_SIN: {
+            float sn, cs;
+#if defined(__CUDA_ARCH__)
+            sincosf(s, &sn, &cs);
+#else
+            sn = sinf(s); cs = cosf(s);
+#endif
+            r.a = sn; r.s1 = cs; r.s2 = -sn; r.s3 = -cs;
+        } break;
+        default: { r.a = s; r.s1 = 1.0f; r.s2 = 0.0f; r.s3 = 0.0f; } break;
+    }
+    return r;
+}
+
+// Load the stored (pre-activation) jet of one hidden unit and turn it into the post-activation
+// jet that feeds the next linear layer:  a, a_d = s1*z_d, a_dd = s2*z_d^2 + s1*z_dd.
+template <int NF, int NS>
+PINN_HD void load_post_jet(const float* __restrict__ row, int RS, int act, float (&a)[1 + NF + NS]) {
+    ActD f = act_from_stored(act, row[0]);
+    a[0] = f.a;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        float zd = row[(1 + d) * RS];
+        a[1 + d] = f.s1 * zd;
+        if (d < NS) {
+            float zdd = row[(1 + NF + d) * RS];
+            a[1 + NF + d] = fmaf(f.s2 * zd, zd, f.s1 * zdd);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Forward: one block of NB*4 output units of a linear layer, all jet channels at once.
+// Wt is the forward layout [n_in][n_out_p4]; weights are read with 128-bit broadcast loads and
+// every loaded weight feeds C FMAs.
+// ----------------------------------------------------------------------------------------------
+template <int NF, int NS, int NB>
+PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
+                              int n_in, const float* __restrict__ in_rows, int RS, int in_act,
+                              float (&acc)[NB * 4][1 + NF + NS]) {
+    constexpr int C = 1 + NF + NS;
+#pragma unroll
+    for (int j = 0; j < NB * 4; ++j) {
+        acc[j][0] = bias[j];
+#pragma unroll
+        for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
+    }
+    for (int k = 0; k < n_in; ++k) {
+        float a[C];
+        load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
+        const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
+#pragma unroll
+        for (int g = 0; g < NB; ++g) {
+            float4 w = wrow[g];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                acc[4 * g + 0][c] = fmaf(w.x, a[c], acc[4 * g + 0][c]);
+                acc[4 * g + 1][c] = fmaf(w.y, a[c], acc[4 * g + 1][c]);
+                acc[4 * g + 2][c] = fmaf(w.z, a[c], acc[4 * g + 2][c]);
+                acc[4 * g + 3][c] = fmaf(w.w, a[c], acc[4 * g + 3][c]);
+            }
+        }
+    }
+}
+
+// First layer: the input jet is (x_k, e_dir, 0), so value channel is a dot product with the
+// coordinates, first-order channels are single weight columns, second-order channels vanish.
+template <int NF, int NS, int NB>
+PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
+                             int n_in, const float* __restrict__ coords, int RS, const int* __restrict__ dir_col,
+                             float (&acc)[NB * 4][1 + NF + NS]) {
+    constexpr int C = 1 + NF + NS;
+#pragma unroll
+    for (int j = 0; j < NB * 4; ++j) {
+        acc[j][0] = bias[j];
+#pragma unroll
+        for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
+    }
+    for (int k = 0; k < n_in; ++k) {
+        float x = coords[(size_t)k * RS];
+        const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
+#pragma unroll
+        for (int g = 0; g < NB; ++g) {
+            float4 w = wrow[g];
+            acc[4 * g + 0][0] = fmaf(w.x, x, acc[4 * g + 0][0]);
+            acc[4 * g + 1][0] = fmaf(w.y, x, acc[4 * g + 1][0]);
+            acc[4 * g + 2][0] = fmaf(w.z, x, acc[4 * g + 2][0]);
+            acc[4 * g + 3][0] = fmaf(w.w, x, acc[4 * g + 3][0]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)dir_col[d] * wt_stride);
+#pragma unroll
+        for (int g = 0; g < NB; ++g) {
+            float4 w = wrow[g];
+            acc[4 * g + 0][1 + d] = w.x; acc[4 * g + 1][1 + d] = w.y;
+            acc[4 * g + 2][1 + d] = w.z; acc[4 * g + 3][1 + d] = w.w;
+        }
+    }
+}
+
+// Store a block of freshly computed pre-activation jets: channel 0 goes through act_store().
+template <int NF, int NS, int NB>
+PINN_HD void store_block(float* __restrict__ out_rows, int RS, int act, int j0, int n_out,
+                         const float (&acc)[NB * 4][1 + NF + NS]) {
+    constexpr int C = 1 + NF + NS;
+#pragma unroll
+    for (int j = 0; j < NB * 4; ++j) {
+        if (j0 + j < n_out) {
+            float* row = out_rows + (size_t)(j0 + j) * C * RS;
+            row[0] = act_store(act, acc[j][0]);
+#pragma unroll
+            for (int c = 1; c < C; ++c) row[(size_t)c * RS] = acc[j][c];
+        }
+    }
+}
+
+// One whole hidden (or input) linear layer, blocked over output units.
+template <int NF, int NS, int JF>
+PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
+                       bool in_is_coords, int in_act, const int* __restrict__ dir_col,
+                       float* __restrict__ out_rows, int RS) {
+    constexpr int NBMAX = JF / 4;
+    const float* Wt = sw + L.wt_s;
+    const float* bias = sw + L.b_s;
+    for (int j0 = 0; j0 < L.n_out; j0 += JF) {
+        int nb = (L.n_out_p4 - j0) / 4;
+        if (nb > NBMAX) nb = NBMAX;
+#define PINN_FWD_CASE(NB)                                                                           \
+        {                                                                                           \
+            float acc[NB * 4][1 + NF + NS];                                                         \
+            if (in_is_coords)                                                                       \
+                fwd_block_input<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,    \
+                                            dir_col, acc);                                          \
+            else                                                                                    \
+                fwd_block_hidden<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,   \
+                                             in_act, acc);                                          \
+            store_block<NF, NS, NB>(out_rows, RS, L.act, j0, L.n_out, acc);                         \
+        }
+        if (NBMAX >= 4 && nb == 4) PINN_FWD_CASE(4)
+        else if (NBMAX >= 3 && nb == 3) PINN_FWD_CASE(3)
+        else if (NBMAX >= 2 && nb == 2) PINN_FWD_CASE(2)
+        else PINN_FWD_CASE(1)
+#undef PINN_FWD_CASE
+    }
+}
+
+// Final linear layer (one output unit, no activation): the network jet N lands in registers.
+template <int NF, int NS>
+PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
+                       bool in_is_coords, int in_act, const int* __restrict__ dir_col, int RS,
+                       float (&N)[1 + NF + NS]) {
+    constexpr int C = 1 + NF + NS;
+    const float* w = sw + L.w_s;            // reverse layout row 0 == the single weight row
+    N[0] = sw[L.b_s];
+#pragma unroll
+    for (int c = 1; c < C; ++c) N[c] = 0.0f;
+    if (in_is_coords) {
+        for (int k = 0; k < L.n_in; ++k) N[0] = fmaf(w[k], in_rows[(size_t)k * RS], N[0]);
+#pragma unroll
+        for (int d = 0; d < NF; ++d) N[1 + d] = w[dir_col[d]];
+    } else {
+        for (int k = 0; k < L.n_in; ++k) {
+            float a[C];
+            load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
+            float wk = w[k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) N[c] = fmaf(wk, a[c], N[c]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Expression programs (residual and initial condition).
+// ----------------------------------------------------------------------------------------------
+PINN_HD float powi_f(float x, int e) {
+    bool neg = e < 0;
+    unsigned n = neg ? (unsigned)(-e) : (unsigned)e;
+    float r = 1.0f, b = x;
+    while (n) { if (n & 1u) r *= b; b *= b; n >>= 1; }
+    return neg ? 1.0f / r : r;
+}
+
+PINN_HD void eval_prog(const PinnInstr* __restrict__ prog, int n, float* __restrict__ scr, int RS,
+                       const float* __restrict__ coords, const float* __restrict__ pvals,
+                       const int* __restrict__ var_off) {
+    for (int i = 0; i < n; ++i) {
+        PinnInstr in = prog[i];
+        float r;
+        switch (in.op) {
+            case PINN_OP_CONST: r = in.imm; break;
+            case PINN_OP_COORD: r = coords[(size_t)in.a * RS]; break;
+            case PINN_OP_VAR:   r = pvals[var_off[in.a]]; break;
+            default: {
+                float x = scr[(size_t)in.a * RS];
+                switch (in.op) {
+                    case PINN_OP_ADD:  r = x + scr[(size_t)in.b * RS]; break;
+                    case PINN_OP_SUB:  r = x - scr[(size_t)in.b * RS]; break;
+                    case PINN_OP_MUL:  r = x * scr[(size_t)in.b * RS]; break;
+                    case PINN_OP_DIV:  r = x / scr[(size_t)in.b * RS]; break;
+                    case PINN_OP_POW:  r = powf(x, scr[(size_t)in.b * RS]); break;
+                    case PINN_OP_NEG:  r = -x; break;
+                    case PINN_OP_MULI: r = x * in.imm; break;
+                    case PINN_OP_ADDI: r = x + in.imm; break;
+                    case PINN_OP_SIN:  r = sinf(x); break;
+                    case PINN_OP_COS:  r = cosf(x); break;
+                    case PINN_OP_TAN:  r = tanf(x); break;
+                    case PINN_OP_EXP:  r = expf(x); break;
+                    case PINN_OP_LOG:  r = logf(x); break;
+                    case PINN_OP_SQRT: r = sqrtf(x); break;
+                    case PINN_OP_TANH: r = tanhf(x); break;
+                    case PINN_OP_SIGMOID: r = 1.0f / (1.0f + expf(-x)); break;
+                    case PINN_OP_RECIP: r = 1.0f / x; break;
+                    case PINN_OP_POWI: r = powi_f(x, (int)in.imm); break;
+                    case PINN_OP_ABS:  r = fabsf(x); break;
+                    case PINN_OP_SIGN: r = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); break;
+                    default:           r = 0.0f; break;
+                }
+            } break;
+        }
+        scr[(size_t)in.dst * RS] = r;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Ansatz (model_torch.py:107-128) forward and adjoint, for axis-aligned directions.
+// ----------------------------------------------------------------------------------------------
+template <int NF, int NS>
+struct AnsatzState {
+    float G, Gd[NF > 0 ? NF : 1], Gdd[NS > 0 ? NS : 1];      // boundary factor jet
+    float S, S1, S2, sig, einv, w;                            // time gate and its t-derivatives
+    float v, vd[NF > 0 ? NF : 1], vdd[NS > 0 ? NS : 1];       // BC-transformed value jet
+};
+
+template <int NF, int NS>
+PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, int RS, float log_scale,
+                            const float (&N)[1 + NF + NS], const float* __restrict__ icj /* C or null */,
+                            AnsatzState<NF, NS>& st, float (&u)[1 + NF + NS]) {
+    // boundary factor G = prod_i (x_i-lo_i)(hi_i-x_i)/(hi_i-lo_i)^2 over spatial dims
+    st.G = 1.0f;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) { st.Gd[d] = 0.0f; if (d < NS) st.Gdd[d] = 0.0f; }
+    if (P.has_bc) {
+        float G = 1.0f;
+        for (int i = 0; i < P.nsp; ++i) {
+            float x = coords[(size_t)i * RS];
+            G *= (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
+        }
+        st.G = G;
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            int k = P.dir_col[d];
+            if (k < P.nsp) {
+                float others = 1.0f;
+                for (int i = 0; i < P.nsp; ++i) {
+                    if (i != k) {
+                        float x = coords[(size_t)i * RS];
+                        others *= (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
+                    }
+                }
+                float xk = coords[(size_t)k * RS];
+                st.Gd[d] = (P.lo[k] + P.hi[k] - 2.0f * xk) * P.inv_w2[k] * others;
+                if (d < NS) st.Gdd[d] = -2.0f * P.inv_w2[k] * others;
+            }
+        }
+        st.v = fmaf(st.G, N[0], P.bc);
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            st.vd[d] = fmaf(st.Gd[d], N[0], st.G * N[1 + d]);
+            if (d < NS)
+                st.vdd[d] = fmaf(st.Gdd[d], N[0], fmaf(2.0f * st.Gd[d], N[1 + d], st.G * N[1 + NF + d]));
+        }
+    } else {
+        st.v = N[0];
+#pragma unroll
+        for (int d = 0; d < NF; ++d) { st.vd[d] = N[1 + d]; if (d < NS) st.vdd[d] = N[1 + NF + d]; }
+    }
+    if (P.has_ic) {
+        float t = coords[(size_t)(P.ndims - 1) * RS];
+        st.einv = expf(-log_scale);
+        st.w = (t - P.t0) * st.einv;
+        st.sig = 1.0f / (1.0f + expf(-st.w));
+        st.S = st.sig - 0.5f;
+        float sp = st.sig * (1.0f - st.sig);
+        st.S1 = sp * st.einv;
+        st.S2 = sp * (1.0f - 2.0f * st.sig) * st.einv * st.einv;
+        u[0] = fmaf(st.S, st.v, icj[0]);
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            bool is_t = (P.dir_col[d] == P.ndims - 1);
+            float Sd = is_t ? st.S1 : 0.0f;
+            u[1 + d] = fmaf(Sd, st.v, fmaf(st.S, st.vd[d], icj[1 + d]));
+            if (d < NS) {
+                float Sdd = is_t ? st.S2 : 0.0f;
+                u[1 + NF + d] = fmaf(Sdd, st.v, fmaf(2.0f * Sd, st.vd[d], fmaf(st.S, st.vdd[d], icj[1 + NF + d])));
+            }
+        }
+    } else {
+        u[0] = st.v;
+#pragma unroll
+        for (int d = 0; d < NF; ++d) { u[1 + d] = st.vd[d]; if (d < NS) u[1 + NF + d] = st.vdd[d]; }
+    }
+}
+
+// Adjoint of the ansatz: ub (d loss / d u-jet) -> Nb (d loss / d N-jet); returns d loss / d log_scale.
+template <int NF, int NS>
+PINN_HD float ansatz_adjoint(const DevPlan& P, const AnsatzState<NF, NS>& st,
+                             const float (&ub)[1 + NF + NS], float (&Nb)[1 + NF + NS]) {
+    float vb, vdb[NF > 0 ? NF : 1], vddb[NS > 0 ? NS : 1];
+    float sbar = 0.0f;
+    if (P.has_ic) {
+        float Sb = ub[0] * st.v, S1b = 0.0f, S2b = 0.0f;
+        vb = st.S * ub[0];
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            bool is_t = (P.dir_col[d] == P.ndims - 1);
+            float Sd = is_t ? st.S1 : 0.0f;
+            vb = fmaf(Sd, ub[1 + d], vb);
+            vdb[d] = st.S * ub[1 + d];
+            Sb = fmaf(ub[1 + d], st.vd[d], Sb);
+            if (is_t) S1b = fmaf(ub[1 + d], st.v, S1b);
+            if (d < NS) {
+                float Sdd = is_t ? st.S2 : 0.0f;
+                float q = ub[1 + NF + d];
+                vb = fmaf(Sdd, q, vb);
+                vdb[d] = fmaf(2.0f * Sd, q, vdb[d]);
+                vddb[d] = st.S * q;
+                Sb = fmaf(q, st.vdd[d], Sb);
+                if (is_t) { S1b = fmaf(2.0f * q, st.vd[d], S1b); S2b = fmaf(q, st.v, S2b); }
+            }
+        }
+        // S = sig(w) - 1/2, S1 = sig'(w) e, S2 = sig''(w) e^2, w = (t - t0) e, e = exp(-s), dw/ds = -w
+        float sg = st.sig, p1 = sg * (1.0f - sg), p2 = p1 * (1.0f - 2.0f * sg),
+              p3 = p1 * fmaf(6.0f * sg, sg - 1.0f, 1.0f);
+        float e = st.einv, w = st.w;
+        float dS = -p1 * w;
+        float dS1 = -e * fmaf(p2, w, p1);
+        float dS2 = -e * e * fmaf(p3, w, 2.0f * p2);
+        sbar = fmaf(Sb, dS, fmaf(S1b, dS1, S2b * dS2));
+    } else {
+        vb = ub[0];
+#pragma unroll
+        for (int d = 0; d < NF; ++d) { vdb[d] = ub[1 + d]; if (d < NS) vddb[d] = ub[1 + NF + d]; }
+    }
+    if (P.has_bc) {
+        float nb0 = st.G * vb;
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            nb0 = fmaf(st.Gd[d], vdb[d], nb0);
+            float nd = st.G * vdb[d];
+            if (d < NS) {
+                nb0 = fmaf(st.Gdd[d], vddb[d], nb0);
+                nd = fmaf(2.0f * st.Gd[d], vddb[d], nd);
+                Nb[1 + NF + d] = st.G * vddb[d];
+            }
+            Nb[1 + d] = nd;
+        }
+        Nb[0] = nb0;
+    } else {
+        Nb[0] = vb;
+#pragma unroll
+        for (int d = 0; d < NF; ++d) { Nb[1 + d] = vdb[d]; if (d < NS) Nb[1 + NF + d] = vddb[d]; }
+    }
+    return sbar;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Reverse sweep.
+// ----------------------------------------------------------------------------------------------
+// Adjoint of one activation: post-activation adjoints (ab) + stored pre jet -> pre adjoints (zb).
+//   zdd_b = s1*add_b ; zd_b = s1*ad_b + 2 s2 zd add_b ; z_b = s1*a_b + sum s2 zd ad_b + (s3 zd^2 + s2 zdd) add_b
+template <int NF, int NS>
+PINN_HD void act_adjoint(const ActD& f, const float (&pre)[1 + NF + NS], const float (&ab)[1 + NF + NS],
+                         float (&zb)[1 + NF + NS]) {
+    float z0 = f.s1 * ab[0];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        float zd = pre[1 + d];
+        float t = f.s2 * zd;
+        z0 = fmaf(t, ab[1 + d], z0);
+        float zdb = f.s1 * ab[1 + d];
+        if (d < NS) {
+            float q = ab[1 + NF + d];
+            zdb = fmaf(2.0f * t, q, zdb);
+            z0 = fmaf(fmaf(f.s3 * zd, zd, f.s2 * pre[1 + NF + d]), q, z0);
+            zb[1 + NF + d] = f.s1 * q;
+        }
+        zb[1 + d] = zdb;
+    }
+    zb[0] = z0;
+}
+
+#if defined(__CUDA_ARCH__)
+// Sum NV per-lane values over the 32 lanes of a warp with a transposing butterfly: on return the
+// lane with (lane % NV) == e holds the total of entry e.  31 shuffles for NV == 32.
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
+#pragma unroll
+    for (int s = 16; s >= NV; s >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+    }
+#pragma unroll
+    for (int s = (NV / 2 < 16 ? NV / 2 : 16); s >= 1; s >>= 1) {
+        bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = up ? v[i] : v[i + s];
+            float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+#endif
+
+// Hand NV per-point contributions to the gradient accumulator: on the GPU they are summed over
+// the warp first and each entry is added once (by one lane); in the host emulation they are
+// added directly.
+template <int NV, class AddFn>
+PINN_HD void emit_entries(float (&v)[NV], AddFn&& add) {
+#if defined(__CUDA_ARCH__)
+    int lane = threadIdx.x & 31;
+    float t = warp_transpose_reduce<NV>(v, lane);
+    if (lane < NV) add(lane, t);
+#else
+    for (int e = 0; e < NV; ++e) add(e, v[e]);
+#endif
+}
+
+struct GradSink {
+    float* wacc;        // accumulator in params layout (+ loss slot) for this warp / CTA
+    bool atomic;        // true when several warps share one accumulator
+    PINN_HD void add(int idx, float val) const {
+#if defined(__CUDA_ARCH__)
+        if (atomic) atomicAdd(wacc + idx, val); else wacc[idx] += val;
+#else
+        wacc[idx] += val;
+#endif
+    }
+};
+
+// Reverse of linear layer L (its output adjoints zb_L are already stored in out_rows):
+//   weight/bias gradients of L and — fused in the same loop — the adjoints of the layer below,
+//   which are pushed through that layer's activation and written over its stored jet in place.
+// JJ = output units handled per reduction batch (4 normally, 1 for the single-output top layer).
+template <int NF, int NS, int JJ>
+PINN_HD void bwd_layer(const DevLayer& L, int below_act, const float* __restrict__ sw,
+                       const float* __restrict__ out_rows, float* __restrict__ in_rows, int RS,
+                       const GradSink& sink) {
+    constexpr int C = 1 + NF + NS;
+    constexpr int JB = 8;
+    const float* W = sw + L.w_s;
+    for (int m0 = 0; m0 < L.n_in; m0 += JB) {
+        float post[JB][C];
+#pragma unroll
+        for (int mm = 0; mm < JB; ++mm) {
+            if (m0 + mm < L.n_in) {
+                load_post_jet<NF, NS>(in_rows + (size_t)(m0 + mm) * C * RS, RS, below_act, post[mm]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) post[mm][c] = 0.0f;
+            }
+        }
+        float acc[JB][C];
+#pragma unroll
+        for (int mm = 0; mm < JB; ++mm)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[mm][c] = 0.0f;
+
+        for (int j0 = 0; j0 < L.n_out; j0 += JJ) {
+            float v[JJ * JB];
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                int j = j0 + jj;
+                float zb[C];
+                if (j < L.n_out) {
+                    const float* row = out_rows + (size_t)j * C * RS;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) zb[c] = row[(size_t)c * RS];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) zb[c] = 0.0f;
+                }
+                const float4* wrow = reinterpret_cast<const float4*>(W + (size_t)j * L.n_in_p8 + m0);
+                float4 w0 = wrow[0], w1 = wrow[1];
+                float w[JB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int mm = 0; mm < JB; ++mm) {
+                    float e = zb[0] * post[mm][0];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        acc[mm][c] = fmaf(w[mm], zb[c], acc[mm][c]);
+                        if (c > 0) e = fmaf(zb[c], post[mm][c], e);
+                    }
+                    v[jj * JB + mm] = e;
+                }
+            }
+            emit_entries<JJ * JB>(v, [&](int e, float t) {
+                int j = j0 + e / JB, m = m0 + e % JB;
+                if (j < L.n_out && m < L.n_in) sink.add(L.w_off + j * L.n_in + m, t);
+            });
+        }
+        // adjoints of the layer below: through its activation, stored in place
+#pragma unroll
+        for (int mm = 0; mm < JB; ++mm) {
+            if (m0 + mm < L.n_in) {
+                float* row = in_rows + (size_t)(m0 + mm) * C * RS;
+                float pre[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
+                ActD f = act_from_stored(below_act, pre[0]);
+                float zb[C];
+                act_adjoint<NF, NS>(f, pre, acc[mm], zb);
+#pragma unroll
+                for (int c = 0; c < C; ++c) row[(size_t)c * RS] = zb[c];
+            }
+        }
+    }
+}
+
+// Bias gradients of layer L: sum over points of the value-channel adjoint.
+template <int NF, int NS>
+PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, int RS, const GradSink& sink) {
+    constexpr int C = 1 + NF + NS;
+    for (int j0 = 0; j0 < L.n_out; j0 += 32) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            v[i] = (j0 + i < L.n_out) ? out_rows[(size_t)(j0 + i) * C * RS] : 0.0f;
+        emit_entries<32>(v, [&](int e, float t) {
+            if (j0 + e < L.n_out) sink.add(L.b_off + j0 + e, t);
+        });
+    }
+}
+
+// Weight gradients of the FIRST linear layer: its input jet is (x, e_dir, 0).
+template <int NF, int NS>
+PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_rows,
+                               const float* __restrict__ coords, int RS, const int* __restrict__ dir_col,
+                               const GradSink& sink) {
+    constexpr int C = 1 + NF + NS;
+    float x[PINN_MAX_DIMS];
+#pragma unroll
+    for (int m = 0; m < PINN_MAX_DIMS; ++m) x[m] = (m < L.n_in) ? coords[(size_t)m * RS] : 0.0f;
+    for (int j0 = 0; j0 < L.n_out; j0 += 4) {
+        float v[4 * PINN_MAX_DIMS];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            int j = j0 + jj;
+            float zb[1 + NF];
+            if (j < L.n_out) {
+                const float* row = out_rows + (size_t)j * C * RS;
+#pragma unroll
+                for (int c = 0; c < 1 + NF; ++c) zb[c] = row[(size_t)c * RS];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 1 + NF; ++c) zb[c] = 0.0f;
+            }
+#pragma unroll
+            for (int m = 0; m < PINN_MAX_DIMS; ++m) {
+                float e = zb[0] * x[m];
+#pragma unroll
+                for (int d = 0; d < NF; ++d) e += (dir_col[d] == m) ? zb[1 + d] : 0.0f;
+                v[jj * PINN_MAX_DIMS + m] = e;
+            }
+        }
+        emit_entries<4 * PINN_MAX_DIMS>(v, [&](int e, float t) {
+            int j = j0 + e / PINN_MAX_DIMS, m = e % PINN_MAX_DIMS;
+            if (j < L.n_out && m < L.n_in) sink.add(L.w_off + j * L.n_in + m, t);
+        });
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// The whole step for ONE point.  `st` is the thread's column of per-point storage (row stride RS).
+// Returns the residual; accumulates loss / log_scale / V partials into the caller's registers.
+// ----------------------------------------------------------------------------------------------
+template <int NF, int NS>
+struct PointPartials { float loss, sbar, vbar[PINN_MAX_VARS]; };
+
+template <int NF, int NS, int JF>
+PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weights */,
+                         const float* __restrict__ pvals /* flat params (for log_scale, V) */,
+                         float* __restrict__ st, int RS, bool valid, float inv_n,
+                         const GradSink& sink, PointPartials<NF, NS>& part) {
+    constexpr int C = 1 + NF + NS;
+    const int Ln = P.n_layers;
+    float* coords = st;
+    float* units = st + (size_t)P.row_units * RS;
+    float* scr = st + (size_t)P.row_scr * RS;
+
+    // ---- forward through the hidden layers ----
+    for (int l = 0; l + 1 < Ln; ++l) {
+        const DevLayer& L = P.layer[l];
+        const float* in_rows = (l == 0) ? coords : units + (size_t)P.layer[l - 1].unit_base * C * RS;
+        int in_act = (l == 0) ? PINN_ACT_NONE : P.layer[l - 1].act;
+        fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, P.dir_col,
+                              units + (size_t)L.unit_base * C * RS, RS);
+    }
+    float N[C];
+    {
+        const DevLayer& L = P.layer[Ln - 1];
+        const float* in_rows = (Ln == 1) ? coords : units + (size_t)P.layer[Ln - 2].unit_base * C * RS;
+        int in_act = (Ln == 1) ? PINN_ACT_NONE : P.layer[Ln - 2].act;
+        fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, P.dir_col, RS, N);
+    }
+
+    // ---- ansatz + residual ----
+    float icj[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) icj[c] = 0.0f;
+    if (P.has_ic) {
+        eval_prog(P.ic, P.n_ic, scr, RS, coords, pvals, P.var_off);
+#pragma unroll
+        for (int c = 0; c < C; ++c) icj[c] = scr[(size_t)P.ic_out[c] * RS];
+    }
+    float log_scale = pvals[P.log_scale_off];
+    AnsatzState<NF, NS> as;
+    float u[C];
+    ansatz_forward<NF, NS>(P, coords, RS, log_scale, N, icj, as, u);
+#pragma unroll
+    for (int c = 0; c < C; ++c) scr[(size_t)c * RS] = u[c];
+    eval_prog(P.eq, P.n_eq, scr, RS, coords, pvals, P.var_off);
+    float r = scr[(size_t)P.eq_out[0] * RS];
+    float rb = valid ? 2.0f * r * inv_n : 0.0f;
+    if (valid) part.loss = fmaf(r * inv_n, r, part.loss);
+    float ub[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) ub[c] = rb * scr[(size_t)P.eq_out[1 + c] * RS];
+#pragma unroll
+    for (int i = 0; i < PINN_MAX_VARS; ++i)
+        if (i < P.n_vars) part.vbar[i] = fmaf(rb, scr[(size_t)P.eq_out[1 + C + i] * RS], part.vbar[i]);
+
+    float Nb[C];
+    part.sbar += ansatz_adjoint<NF, NS>(P, as, ub, Nb);
+
+    // ---- reverse sweep ----
+    {
+        const DevLayer& L = P.layer[Ln - 1];
+        float* out_rows = units + (size_t)L.unit_base * C * RS;
+#pragma unroll
+        for (int c = 0; c < C; ++c) out_rows[(size_t)c * RS] = Nb[c];
+    }
+    for (int l = Ln - 1; l >= 1; --l) {
+        const DevLayer& L = P.layer[l];
+        float* out_rows = units + (size_t)L.unit_base * C * RS;
+        float* in_rows = units + (size_t)P.layer[l - 1].unit_base * C * RS;
+        if (L.n_out == 1) bwd_layer<NF, NS, 1>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
+        else              bwd_layer<NF, NS, 4>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
+        bias_grad<NF, NS>(L, out_rows, RS, sink);
+    }
+    {
+        const DevLayer& L = P.layer[0];
+        float* out_rows = units + (size_t)L.unit_base * C * RS;
+        wgrad_input_layer<NF, NS>(L, out_rows, coords, RS, P.dir_col, sink);
+        bias_grad<NF, NS>(L, out_rows, RS, sink);
+    }
+    return r;
+}
+
+// Forward-only value u(x) for one point (predict path): no jets (NF = NS = 0).
+template <int JF>
+PINN_HD float point_forward(const DevPlan& P, const float* __restrict__ sw, const float* __restrict__ pvals,
+                            float* __restrict__ st, int RS, int row_scr_fwd) {
+    const int Ln = P.n_layers;
+    float* coords = st;
+    float* units = st + (size_t)P.row_units * RS;
+    float* scr = st + (size_t)row_scr_fwd * RS;
+    int dummy_dir[1] = {0};
+    for (int l = 0; l + 1 < Ln; ++l) {
+        const DevLayer& L = P.layer[l];
+        const float* in_rows = (l == 0) ? coords : units + (size_t)P.layer[l - 1].unit_base * RS;
+        int in_act = (l == 0) ? PINN_ACT_NONE : P.layer[l - 1].act;
+        fwd_layer<0, 0, JF>(L, sw, in_rows, l == 0, in_act, dummy_dir, units + (size_t)L.unit_base * RS, RS);
+    }
+    float N[1];
+    {
+        const DevLayer& L = P.layer[Ln - 1];
+        const float* in_rows = (Ln == 1) ? coords : units + (size_t)P.layer[Ln - 2].unit_base * RS;
+        int in_act = (Ln == 1) ? PINN_ACT_NONE : P.layer[Ln - 2].act;
+        fwd_final<0, 0>(L, sw, in_rows, Ln == 1, in_act, dummy_dir, RS, N);
+    }
+    float icj[1] = {0.0f};
+    if (P.has_ic) {
+        eval_prog(P.ic, P.n_ic, scr, RS, coords, pvals, P.var_off);
+        icj[0] = scr[(size_t)P.ic_out[0] * RS];
+    }
+    AnsatzState<0, 0> as;
+    float u[1];
+    ansatz_forward<0, 0>(P, coords, RS, pvals[P.log_scale_off], N, icj, as, u);
+    return u[0];
+}
+
+}  // namespace pinn

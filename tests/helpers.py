@@ -1,0 +1,31 @@
+""" Shared helpers of the test-suite (oracle side). """
+import os
+
+import numpy as np
+import torch
+
+import problems as P
+from oracle import autograd_port as ap
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def oracle_problem(name, dtype=torch.float32, params=None):
+    cfg = P.PROBLEMS[name]
+    prob = ap.Problem(lambda u, *xs, D, V: cfg['equation'](u, *xs, D=D, V=V),
+                      ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=cfg['ic'],
+                      boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
+                      activation=cfg['activation'], dtype=dtype, variables=cfg.get('variables'))
+    if params is not None:
+        prob.load_flat(torch.as_tensor(params))
+    return prob
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

@@ -1,0 +1,115 @@
+""" Problem registry shared by oracle/make_golden.py, the oracle tests and the GPU parity tests.
+
+Equations are written once, token-agnostic: `eq(u, *xs, D=..., V=...)`; the harness binds D/V of
+whichever implementation is under test (reference, oracle port, pydens_b200).  `V(name, init)`.
+
+BASELINE.json configs: cfg1/cfg2 = poisson2d, cfg3 = ode_param, cfg4 = heat2d, cfg5 = wave3d.
+The others cover the tutorial's remaining problems and the corner cases of the ansatz / programs.
+"""
+import math
+
+import numpy as np
+import torch
+
+PI = math.pi
+
+
+def _poisson2d(f, x, y, D, V):                       # README.md:36-37
+    return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
+
+
+def _ode_param(f, x, e, D, V):                       # README.md:78-79
+    return D(f, x) - e * np.pi * torch.cos(e * np.pi * x)
+
+
+def _heat2d(f, x, y, t, D, V):                       # tutorial heat eq. without the parameter
+    return D(D(f, x), x) + D(D(f, y), y) - D(f, t)
+
+
+def _heat_param(f, x, y, t, a, D, V):                # tutorial: `- a * D(f, t)`
+    return D(D(f, x), x) + D(D(f, y), y) - a * D(f, t)
+
+
+def _wave3d(f, x, y, z, t, D, V):                    # BASELINE.json cfg5
+    return D(D(f, t), t) - (D(D(f, x), x) + D(D(f, y), y) + D(D(f, z), z))
+
+
+def _ode_var(f, x, D, V):                            # tutorial `odevar`
+    return D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x) + V('new_var', 1.0)
+
+
+def _ode_tanh(f, x, D, V):                           # tutorial first example
+    return D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x)
+
+
+def _burgers(f, x, t, D, V):
+    return D(f, t) + f * D(f, x) - 0.01 * D(D(f, x), x)
+
+
+def _nonlinear(f, x, y, D, V):
+    fx = D(f, x)
+    return (fx * torch.exp(-x) + f ** 2 - torch.sqrt(x + 1.0) + torch.log(x + 2.0) / (y + 1.0)
+            + torch.tanh(D(D(f, y), y)) * 0.5 - (2.0 - y) ** 3 + torch.cos(f) / 3.0 + abs(fx) * 0.1)
+
+
+def _ic_heat(x, y):
+    return 10 * x * y * (1 - x) * (1 - y)
+
+
+def _ic_wave(x, y, z):
+    return torch.sin(PI * x) * torch.sin(PI * y) * torch.sin(PI * z)
+
+
+def _ic_burgers(x):
+    return 0.3 * torch.sin(x) + 0.1
+
+
+PROBLEMS = {
+    # name: dict(equation, ndims, nparams, ic, bc, domain, features, activation, variables, ranges, log_scale)
+    'poisson2d': dict(equation=_poisson2d, ndims=2, nparams=0, ic=None, bc=1, domain=(0, 1),
+                      features=[10, 12, 15, 1], activation='Tanh', layout='fa fa fa f',
+                      ranges=[(0, 1), (0, 1)]),
+    'ode_param': dict(equation=_ode_param, ndims=1, nparams=1, ic=1.0, bc=None, domain=(0, 1),
+                      features=[20, 30, 1], activation='Sigmoid', layout='fafaf',
+                      ranges=[(0, 1), (1, 5)]),
+    'heat2d': dict(equation=_heat2d, ndims=3, nparams=0, ic=_ic_heat, bc=0, domain=(0, 1),
+                   features=[30, 40, 1], activation='Sigmoid', layout='fafaf',
+                   ranges=[(0, 1), (0, 1), (0, .5)]),
+    'heat_param': dict(equation=_heat_param, ndims=3, nparams=1, ic=_ic_heat, bc=0, domain=(0, 1),
+                       features=[30, 40, 1], activation='Sigmoid', layout='fafaf',
+                       ranges=[(0, 1), (0, 1), (0, .5), (.1, 4)]),
+    'wave3d': dict(equation=_wave3d, ndims=4, nparams=0, ic=_ic_wave, bc=0, domain=(0, 1),
+                   features=[64, 64, 64, 64, 1], activation='Tanh', layout='fafafafaf',
+                   ranges=[(0, 1)] * 4),
+    'ode_var': dict(equation=_ode_var, ndims=1, nparams=0, ic=1, bc=None, domain=(0, 1),
+                    features=[20, 30, 1], activation='Sigmoid', layout='fafaf',
+                    variables={'new_var': 1.0}, ranges=[(0, 1)]),
+    'ode_tanh': dict(equation=_ode_tanh, ndims=1, nparams=0, ic=.5, bc=None, domain=(0, 1),
+                     features=[12, 10, 1], activation='Tanh', layout='fafaf', ranges=[(0, 1)]),
+    'burgers': dict(equation=_burgers, ndims=2, nparams=0, ic=_ic_burgers, bc=0.5,
+                    domain=[(-1, 2), (0, 3)], features=[8, 9, 1], activation='Tanh', layout='fafaf',
+                    ranges=[(-1, 2), (0, 3)], log_scale=0.3),
+    'nonlinear': dict(equation=_nonlinear, ndims=2, nparams=0, ic=None, bc=None, domain=(0, 1),
+                      features=[7, 5, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1), (0, 1)]),
+}
+
+GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
+                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64}
+
+# problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
+GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
+               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05)}
+
+
+def make_points(name, batch, seed):
+    """ Deterministic explicit points: uniform in the problem's per-column ranges, fp32. """
+    cfg = PROBLEMS[name]
+    rng = np.random.RandomState(seed)
+    cols = [rng.uniform(lo, hi, size=(batch, 1)) for lo, hi in cfg['ranges']]
+    return np.concatenate(cols, axis=1).astype(np.float32)
+
+
+def bind(name, D, V):
+    """ Equation callable with the reference signature `equation(u, *xs)`. """
+    eq = PROBLEMS[name]['equation']
+    return lambda u, *xs: eq(u, *xs, D=D, V=V)
