@@ -24,6 +24,7 @@
 #else
 #define PINN_HD inline
 #define PINN_D  inline
+struct float4 { float x, y, z, w; };      // host emulation build only
 #endif
 
 namespace pinn {

@@ -18,241 +18,10 @@
 #include <string.h>
 #include <new>
 
-#include "pinn_device.cuh"
+#include "pinn_step_kernel.cuh"
+#include "pinn_host_plan.h"
 
 namespace pinn {
-
-constexpr int RS = 32;                    // row stride of per-point storage: one warp tile
-
-struct StepArgs {
-    const DevPlan* plan;
-    const float* params;
-    const float* points;
-    uint64_t seed;
-    const uint64_t* step_ptr;
-    uint64_t step_val;
-    uint64_t point_offset;
-    long long n_points;
-    float inv_n;
-    float* out;
-    float* residual;
-    float* partials;
-    unsigned int* ticket;
-    float* spill;
-    int n_wacc;                            // accumulator copies in smem: warps per CTA, or 1 (atomics)
-    int rows_total;
-};
-
-struct FwdArgs {
-    const DevPlan* plan;
-    const float* params;
-    const float* points;
-    long long n_points;
-    float* u_out;
-    float* spill;
-    int rows_total;
-    int row_scr;
-};
-
-// ---- PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared) ---------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    return v;
-}
-
-// Shared-memory carve-up (in floats) common to both kernels.
-struct SmemLayout {
-    int plan_f, weights_f, wacc_f, bar_f, storage_f, total_f;
-};
-__host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
-__host__ __device__ inline SmemLayout smem_layout(int weights_floats, int n_out_floats, int n_wacc,
-                                                  int storage_floats) {
-    SmemLayout L;
-    L.plan_f = 0;
-    L.weights_f = align4((int)(sizeof(DevPlan) / 4));
-    L.wacc_f = L.weights_f + align4(weights_floats);
-    L.bar_f = L.wacc_f + align4(n_out_floats * n_wacc);
-    L.storage_f = L.bar_f + 4;
-    L.total_f = L.storage_f + align4(storage_floats);
-    return L;
-}
-
-// Stage plan + parameters into shared memory.  Returns with __syncthreads() done.
-__device__ __forceinline__ void stage_plan_and_weights(float* smem, const SmemLayout& SL, const DevPlan* gplan,
-                                                       const float* params) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // plan copy
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(gplan);
-        uint4* dst = reinterpret_cast<uint4*>(smem + SL.plan_f);
-        for (int i = tid; i < (int)(sizeof(DevPlan) / 16); i += nt) dst[i] = src[i];
-    }
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SL.bar_f);
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem + SL.plan_f);
-    float* stage = smem + SL.storage_f;           // parameters land here first
-    if (tid == 0) {
-        uint32_t bytes = (uint32_t)P.n_params * 4u;
-        mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(stage, params, bytes, bar);
-    }
-    float* sw = smem + SL.weights_f;
-    for (int i = tid; i < P.weights_floats; i += nt) sw[i] = 0.0f;
-    mbar_wait(bar, 0);
-    __syncthreads();
-    for (int l = 0; l < P.n_layers; ++l) {
-        const DevLayer& L = P.layer[l];
-        const int n = L.n_in * L.n_out;
-        for (int i = tid; i < n; i += nt) {
-            int j = i / L.n_in, k = i - j * L.n_in;
-            float w = stage[L.w_off + i];
-            sw[L.wt_s + k * L.n_out_p4 + j] = w;
-            sw[L.w_s + j * L.n_in_p8 + k] = w;
-        }
-        for (int j = tid; j < L.n_out; j += nt) sw[L.b_s + j] = stage[L.b_off + j];
-    }
-    __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------------
-// The fit-step kernel.
-// ---------------------------------------------------------------------------------------------------
-template <int NF, int NS, bool GMEM, int MAXT, int JF>
-__global__ void __launch_bounds__(MAXT, 1) step_kernel(const StepArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-
-    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem);
-    // sizes needed for the carve-up come straight from the global plan (uniform loads)
-    const int n_out_floats = a.plan->n_params + 4;
-    const SmemLayout SL = smem_layout(a.plan->weights_floats, n_out_floats, a.n_wacc,
-                                      GMEM ? a.plan->n_params : max(a.plan->n_params, a.rows_total * RS * nwarps));
-    stage_plan_and_weights(smem, SL, a.plan, a.params);
-    const float* sw = smem + SL.weights_f;
-    float* wacc_all = smem + SL.wacc_f;
-    for (int i = tid; i < n_out_floats * a.n_wacc; i += blockDim.x) wacc_all[i] = 0.0f;
-    __syncthreads();
-
-    GradSink sink;
-    sink.atomic = (a.n_wacc == 1 && nwarps > 1);
-    sink.wacc = wacc_all + (a.n_wacc == 1 ? 0 : warp * n_out_floats);
-
-    const long long gw = (long long)blockIdx.x * nwarps + warp;         // global warp id
-    const long long total_warps = (long long)gridDim.x * nwarps;
-    float* st = (GMEM ? a.spill + (size_t)gw * a.rows_total * RS : smem + SL.storage_f + (size_t)warp * a.rows_total * RS) + lane;
-
-    const uint64_t step = a.step_ptr ? *a.step_ptr : a.step_val;
-    const long long n_tiles = (a.n_points + 31) / 32;
-    PointPartials<NF, NS> part;
-    part.loss = 0.0f; part.sbar = 0.0f;
-#pragma unroll
-    for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
-
-    for (long long tile = gw; tile < n_tiles; tile += total_warps) {
-        const long long pl = tile * 32 + lane;
-        const bool valid = pl < a.n_points;
-        const long long pe = valid ? pl : a.n_points - 1;     // masked lanes replay the last point
-        if (a.points) {
-            const float* src = a.points + (size_t)pe * P.total;
-            for (int k = 0; k < P.total; ++k) st[k * RS] = __ldg(src + k);
-        } else {
-            const uint64_t gidx = a.point_offset + (uint64_t)pe;
-            const uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16);
-            Philox4 b0 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
-                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            Philox4 b1 = b0;
-            if (P.total > 4)
-                b1 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3 | 1u,
-                                   (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            for (int k = 0; k < P.total; ++k) st[k * RS] = sample_column(P.cols[k], k, gidx, step, a.seed, b0, b1);
-        }
-        float r = point_step<NF, NS, JF>(P, sw, a.params, st, RS, valid, a.inv_n, sink, part);
-        if (a.residual && valid) a.residual[pl] = r;
-    }
-
-    // per-thread scalars -> accumulator
-    {
-        float v = warp_sum(part.loss);
-        if (lane == 0) sink.add(P.n_params, v);
-        v = warp_sum(part.sbar);
-        if (lane == 0) sink.add(P.log_scale_off, v);
-#pragma unroll
-        for (int i = 0; i < PINN_MAX_VARS; ++i) {
-            if (i < P.n_vars) {
-                float t = warp_sum(part.vbar[i]);
-                if (lane == 0) sink.add(P.var_off[i], t);
-            }
-        }
-    }
-    __syncthreads();
-
-    // CTA partial -> global, then the last CTA folds all partials in block order
-    float* mine = a.partials + (size_t)blockIdx.x * n_out_floats;
-    for (int i = tid; i < n_out_floats; i += blockDim.x) {
-        float s = 0.0f;
-        for (int w = 0; w < a.n_wacc; ++w) s += wacc_all[w * n_out_floats + i];
-        mine[i] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    __shared__ unsigned int s_last;
-    if (tid == 0) {
-        unsigned int t = atomicAdd(a.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        for (int i = tid; i < n_out_floats; i += blockDim.x) {
-            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-            int b = 0;
-            const float* src = a.partials + i;
-            for (; b + 3 < (int)gridDim.x; b += 4) {
-                s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
-                s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
-                s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
-                s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
-            }
-            for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
-            a.out[i] = (s0 + s1) + (s2 + s3);
-        }
-        if (tid == 0) *a.ticket = 0u;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Forward-only kernel (predict): u for explicit points.
@@ -335,43 +104,16 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(PINN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
-typedef void (*StepKernelFn)(const StepArgs);
-
-struct Variant {
-    int nf, ns;
-    StepKernelFn smem_fn, gmem_fn;
-    int maxt;
-};
-
-template <int NF, int NS>
-struct VariantCfg {
-    static constexpr int C = 1 + NF + NS;
-    static constexpr int MAXT = (C <= 3) ? 512 : 256;
-    static constexpr int JF = 16;
-};
-
-template <int NF, int NS>
-static Variant make_variant() {
-    using Cfg = VariantCfg<NF, NS>;
-    Variant v;
-    v.nf = NF; v.ns = NS;
-    v.smem_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF>;
-    v.gmem_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF>;
-    v.maxt = Cfg::MAXT;
-    return v;
-}
-
 static const Variant* find_variant(int nf, int ns) {
-    static const Variant table[] = {
-        make_variant<0, 0>(),
-        make_variant<1, 0>(), make_variant<1, 1>(),
-        make_variant<2, 0>(), make_variant<2, 1>(), make_variant<2, 2>(),
-        make_variant<3, 0>(), make_variant<3, 1>(), make_variant<3, 2>(), make_variant<3, 3>(),
-        make_variant<4, 0>(), make_variant<4, 1>(), make_variant<4, 2>(), make_variant<4, 3>(), make_variant<4, 4>(),
-    };
-    for (const Variant& v : table)
-        if (v.nf == nf && v.ns == ns) return &v;
-    return nullptr;
+    if (ns < 0 || ns > nf) return nullptr;
+    switch (nf) {
+        case 0: return pinn_variants_nf0(ns);
+        case 1: return pinn_variants_nf1(ns);
+        case 2: return pinn_variants_nf2(ns);
+        case 3: return pinn_variants_nf3(ns);
+        case 4: return pinn_variants_nf4(ns);
+        default: return nullptr;
+    }
 }
 
 struct PinnPlan {
@@ -392,119 +134,32 @@ struct PinnPlan {
     bool cols_set;
 };
 
-static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 extern "C" const char* pinn_last_error(void) { return g_err; }
 extern "C" int pinn_abi_version(void) { return PINN_ABI_VERSION; }
 
-static int validate_prog(const PinnInstr* prog, int n, int n_slots, int total, int n_vars, const char* name) {
-    if (n < 0 || n > PINN_MAX_PROG) return fail(PINN_E_INVALID, "%s: %d instructions (max %d)", name, n, PINN_MAX_PROG);
-    for (int i = 0; i < n; ++i) {
-        const PinnInstr& in = prog[i];
-        if (in.op >= PINN_OP_COUNT_) return fail(PINN_E_INVALID, "%s[%d]: bad opcode %d", name, i, in.op);
-        if (in.dst >= n_slots) return fail(PINN_E_INVALID, "%s[%d]: dst slot %d >= n_slots %d", name, i, in.dst, n_slots);
-        if (in.op == PINN_OP_COORD && in.a >= total) return fail(PINN_E_INVALID, "%s[%d]: coord %d", name, i, in.a);
-        if (in.op == PINN_OP_VAR && in.a >= n_vars) return fail(PINN_E_INVALID, "%s[%d]: var %d", name, i, in.a);
-        if (in.op >= PINN_OP_ADD) {
-            if (in.a >= n_slots) return fail(PINN_E_INVALID, "%s[%d]: src slot", name, i);
-            bool binary = in.op == PINN_OP_ADD || in.op == PINN_OP_SUB || in.op == PINN_OP_MUL ||
-                          in.op == PINN_OP_DIV || in.op == PINN_OP_POW;
-            if (binary && in.b >= n_slots) return fail(PINN_E_INVALID, "%s[%d]: src slot", name, i);
-        }
-    }
-    return PINN_OK;
-}
-
 extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     if (!s || !out) return fail(PINN_E_INVALID, "null argument");
-    if (s->abi_version != PINN_ABI_VERSION)
-        return fail(PINN_E_INVALID, "spec abi_version %d != library %d", s->abi_version, PINN_ABI_VERSION);
-    const int Ln = s->n_layers;
-    if (Ln < 1 || Ln > PINN_MAX_LAYERS) return fail(PINN_E_INVALID, "n_layers %d", Ln);
-    const int total = s->ndims + s->nparams;
-    if (s->ndims < 1 || s->nparams < 0 || total > PINN_MAX_DIMS) return fail(PINN_E_INVALID, "ndims/nparams");
-    if (s->widths[0] != total) return fail(PINN_E_INVALID, "widths[0]=%d != ndims+nparams=%d", s->widths[0], total);
-    if (s->widths[Ln] != 1) return fail(PINN_E_UNSUPPORTED, "output width %d (must be 1)", s->widths[Ln]);
-    if (s->act[Ln - 1] != PINN_ACT_NONE) return fail(PINN_E_UNSUPPORTED, "activation after the last layer");
-    if (s->n_params <= 0 || (s->n_params & 3)) return fail(PINN_E_INVALID, "n_params must be a positive multiple of 4");
-    if (s->nf < 0 || s->nf > PINN_MAX_DIRS || s->ns < 0 || s->ns > s->nf) return fail(PINN_E_INVALID, "jet set nf=%d ns=%d", s->nf, s->ns);
-    if (s->n_vars < 0 || s->n_vars > PINN_MAX_VARS) return fail(PINN_E_INVALID, "n_vars");
-    const int C = 1 + s->nf + s->ns;
-    for (int d = 0; d < s->nf; ++d)
-        if (s->dir_col[d] < 0 || s->dir_col[d] >= total) return fail(PINN_E_INVALID, "dir_col[%d]", d);
-    if (s->n_slots < C || s->n_slots > PINN_MAX_SLOTS) return fail(PINN_E_INVALID, "n_slots %d", s->n_slots);
-    int rc;
-    if ((rc = validate_prog(s->eq_prog, s->n_eq, s->n_slots, total, s->n_vars, "eq_prog"))) return rc;
-    if ((rc = validate_prog(s->ic_prog, s->n_ic, s->n_slots, total, 0, "ic_prog"))) return rc;
-    for (int i = 0; i < 1 + C + s->n_vars; ++i)
-        if (s->eq_out[i] < 0 || s->eq_out[i] >= s->n_slots) return fail(PINN_E_INVALID, "eq_out[%d]", i);
-    if (s->has_ic)
-        for (int c = 0; c < C; ++c)
-            if (s->ic_out[c] < 0 || s->ic_out[c] >= s->n_slots) return fail(PINN_E_INVALID, "ic_out[%d]", c);
-    const Variant* var = find_variant(s->nf, s->ns);
-    if (!var) return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns);
-
+    const Variant* var = nullptr;
     PinnPlan* p = new (std::nothrow) PinnPlan();
     if (!p) return fail(PINN_E_INVALID, "out of memory");
+    {
+        char msg[256];
+        int rc = build_dev_plan(s, p->h, p->fwd_rows, p->fwd_row_scr, msg, sizeof(msg));
+        if (rc) { delete p; return fail(rc, "%s", msg); }
+    }
+    var = find_variant(s->nf, s->ns);
+    if (!var) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns); }
     p->spec = *s;
     p->device = device;
     p->var = var;
     p->d = nullptr;
     p->cols_set = false;
     DevPlan& h = p->h;
-    memset(&h, 0, sizeof(h));
-    h.n_layers = Ln; h.total = total; h.ndims = s->ndims; h.nparams = s->nparams;
-    h.has_bc = s->has_bc ? 1 : 0; h.has_ic = s->has_ic ? 1 : 0;
-    h.nsp = s->has_ic ? s->ndims - 1 : s->ndims;
-    h.nf = s->nf; h.ns = s->ns; h.n_params = s->n_params; h.log_scale_off = s->log_scale_off;
-    h.n_vars = s->n_vars; h.n_eq = s->n_eq; h.n_ic = s->has_ic ? s->n_ic : 0; h.n_slots = s->n_slots;
-    h.bc = s->bc_value;
-    h.t0 = s->dom_lo[s->ndims - 1];
-    for (int d = 0; d < PINN_MAX_DIRS; ++d) h.dir_col[d] = d < s->nf ? s->dir_col[d] : 0;
-    for (int i = 0; i < PINN_MAX_VARS; ++i) h.var_off[i] = i < s->n_vars ? s->var_off[i] : 0;
-    for (int i = 0; i < PINN_MAX_DIMS; ++i) {
-        h.lo[i] = s->dom_lo[i]; h.hi[i] = s->dom_hi[i];
-        float w = s->dom_hi[i] - s->dom_lo[i];
-        h.inv_w2[i] = (i < s->ndims && w != 0.0f) ? 1.0f / (w * w) : 0.0f;
-        h.cols[i].kind = PINN_COL_UNIFORM; h.cols[i].a = 0.0f; h.cols[i].b = 1.0f;
-    }
-    memcpy(h.eq_out, s->eq_out, sizeof(h.eq_out));
-    memcpy(h.ic_out, s->ic_out, sizeof(h.ic_out));
-    memcpy(h.eq, s->eq_prog, sizeof(h.eq));
-    memcpy(h.ic, s->ic_prog, sizeof(h.ic));
-    if (s->log_scale_off < 0 || s->log_scale_off >= s->n_params) { delete p; return fail(PINN_E_INVALID, "log_scale_off"); }
-
-    int sw = 0, units = 0;
-    long long macs = 0;
-    for (int l = 0; l < Ln; ++l) {
-        DevLayer& L = h.layer[l];
-        L.n_in = s->widths[l]; L.n_out = s->widths[l + 1]; L.act = s->act[l];
-        if (L.n_in < 1 || L.n_out < 1) { delete p; return fail(PINN_E_INVALID, "layer %d width", l); }
-        if (L.act < 0 || L.act > PINN_ACT_SIN) { delete p; return fail(PINN_E_INVALID, "layer %d activation", l); }
-        L.w_off = s->w_off[l]; L.b_off = s->b_off[l];
-        if (L.w_off < 0 || L.w_off + L.n_in * L.n_out > s->n_params || L.b_off < 0 || L.b_off + L.n_out > s->n_params) {
-            delete p; return fail(PINN_E_INVALID, "layer %d offsets out of range", l);
-        }
-        L.n_out_p4 = round_up(L.n_out, 4);
-        L.n_in_p8 = round_up(L.n_in, 8);
-        L.wt_s = sw; sw += L.n_in * L.n_out_p4;
-        L.w_s = sw;  sw += L.n_out_p4 * L.n_in_p8;
-        L.b_s = sw;  sw += round_up(L.n_out_p4, 16);     // forward blocks read bias[j0 .. j0+15]
-        L.unit_base = units; units += L.n_out;
-        macs += (long long)L.n_in * L.n_out;
-    }
-    // forward weight rows are read 16 floats at a time from j0: pad the tail
-    sw += 16;
-    h.weights_floats = round_up(sw, 4);
-    h.n_units = units;
-    h.row_units = total;
-    h.row_scr = total + units * C;
-    h.rows_total = h.row_scr + s->n_slots;
-    p->fwd_row_scr = total + units;
-    p->fwd_rows = p->fwd_row_scr + s->n_slots;
+    cudaError_t e;
 
     // ---- device queries and launch configuration ----
-    cudaError_t e = cudaSetDevice(device);
+    e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); }
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
@@ -574,7 +229,6 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     if (e != cudaSuccess) { cudaFree(p->d); delete p; return fail(PINN_E_CUDA, "cudaMemcpy(plan): %s", cudaGetErrorString(e)); }
     for (int i = 0; i < PINN_MAX_DIMS; ++i) p->cur_cols[i] = h.cols[i];
     p->cols_set = true;
-    (void)macs;
     *out = p;
     return PINN_OK;
 }

@@ -1,0 +1,278 @@
+// pinn_step_kernel.cuh — the fused fit-step kernel template and its shared-memory staging helpers.
+// Included by pinn_kernels.cu (host API, forward/sampling kernels) and by the per-NF translation
+// units pinn_variants_nf*.cu, which only instantiate step_kernel so the build can run in parallel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pinn_device.cuh"
+
+namespace pinn {
+
+constexpr int RS = 32;                    // row stride of per-point storage: one warp tile
+
+struct StepArgs {
+    const DevPlan* plan;
+    const float* params;
+    const float* points;
+    uint64_t seed;
+    const uint64_t* step_ptr;
+    uint64_t step_val;
+    uint64_t point_offset;
+    long long n_points;
+    float inv_n;
+    float* out;
+    float* residual;
+    float* partials;
+    unsigned int* ticket;
+    float* spill;
+    int n_wacc;                            // accumulator copies in smem: warps per CTA, or 1 (atomics)
+    int rows_total;
+};
+
+struct FwdArgs {
+    const DevPlan* plan;
+    const float* params;
+    const float* points;
+    long long n_points;
+    float* u_out;
+    float* spill;
+    int rows_total;
+    int row_scr;
+};
+
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// Shared-memory carve-up (in floats) common to both kernels.
+struct SmemLayout {
+    int plan_f, weights_f, wacc_f, bar_f, storage_f, total_f;
+};
+__host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline SmemLayout smem_layout(int weights_floats, int n_out_floats, int n_wacc,
+                                                  int storage_floats) {
+    SmemLayout L;
+    L.plan_f = 0;
+    L.weights_f = align4((int)(sizeof(DevPlan) / 4));
+    L.wacc_f = L.weights_f + align4(weights_floats);
+    L.bar_f = L.wacc_f + align4(n_out_floats * n_wacc);
+    L.storage_f = L.bar_f + 4;
+    L.total_f = L.storage_f + align4(storage_floats);
+    return L;
+}
+
+// Stage plan + parameters into shared memory.  Returns with __syncthreads() done.
+__device__ __forceinline__ void stage_plan_and_weights(float* smem, const SmemLayout& SL, const DevPlan* gplan,
+                                                       const float* params) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // plan copy
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(gplan);
+        uint4* dst = reinterpret_cast<uint4*>(smem + SL.plan_f);
+        for (int i = tid; i < (int)(sizeof(DevPlan) / 16); i += nt) dst[i] = src[i];
+    }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SL.bar_f);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem + SL.plan_f);
+    float* stage = smem + SL.storage_f;           // parameters land here first
+    if (tid == 0) {
+        uint32_t bytes = (uint32_t)P.n_params * 4u;
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(stage, params, bytes, bar);
+    }
+    float* sw = smem + SL.weights_f;
+    for (int i = tid; i < P.weights_floats; i += nt) sw[i] = 0.0f;
+    mbar_wait(bar, 0);
+    __syncthreads();
+    for (int l = 0; l < P.n_layers; ++l) {
+        const DevLayer& L = P.layer[l];
+        const int n = L.n_in * L.n_out;
+        for (int i = tid; i < n; i += nt) {
+            int j = i / L.n_in, k = i - j * L.n_in;
+            float w = stage[L.w_off + i];
+            sw[L.wt_s + k * L.n_out_p4 + j] = w;
+            sw[L.w_s + j * L.n_in_p8 + k] = w;
+        }
+        for (int j = tid; j < L.n_out; j += nt) sw[L.b_s + j] = stage[L.b_off + j];
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The fit-step kernel.
+// ---------------------------------------------------------------------------------------------------
+template <int NF, int NS, bool GMEM, int MAXT, int JF>
+__global__ void __launch_bounds__(MAXT, 1) step_kernel(const StepArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem);
+    // sizes needed for the carve-up come straight from the global plan (uniform loads)
+    const int n_out_floats = a.plan->n_params + 4;
+    const SmemLayout SL = smem_layout(a.plan->weights_floats, n_out_floats, a.n_wacc,
+                                      GMEM ? a.plan->n_params : max(a.plan->n_params, a.rows_total * RS * nwarps));
+    stage_plan_and_weights(smem, SL, a.plan, a.params);
+    const float* sw = smem + SL.weights_f;
+    float* wacc_all = smem + SL.wacc_f;
+    for (int i = tid; i < n_out_floats * a.n_wacc; i += blockDim.x) wacc_all[i] = 0.0f;
+    __syncthreads();
+
+    GradSink sink;
+    sink.atomic = (a.n_wacc == 1 && nwarps > 1);
+    sink.wacc = wacc_all + (a.n_wacc == 1 ? 0 : warp * n_out_floats);
+
+    const long long gw = (long long)blockIdx.x * nwarps + warp;         // global warp id
+    const long long total_warps = (long long)gridDim.x * nwarps;
+    float* st = (GMEM ? a.spill + (size_t)gw * a.rows_total * RS : smem + SL.storage_f + (size_t)warp * a.rows_total * RS) + lane;
+
+    const uint64_t step = a.step_ptr ? *a.step_ptr : a.step_val;
+    const long long n_tiles = (a.n_points + 31) / 32;
+    PointPartials<NF, NS> part;
+    part.loss = 0.0f; part.sbar = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
+
+    for (long long tile = gw; tile < n_tiles; tile += total_warps) {
+        const long long pl = tile * 32 + lane;
+        const bool valid = pl < a.n_points;
+        const long long pe = valid ? pl : a.n_points - 1;     // masked lanes replay the last point
+        if (a.points) {
+            const float* src = a.points + (size_t)pe * P.total;
+            for (int k = 0; k < P.total; ++k) st[k * RS] = __ldg(src + k);
+        } else {
+            const uint64_t gidx = a.point_offset + (uint64_t)pe;
+            const uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16);
+            Philox4 b0 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            Philox4 b1 = b0;
+            if (P.total > 4)
+                b1 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3 | 1u,
+                                   (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            for (int k = 0; k < P.total; ++k) st[k * RS] = sample_column(P.cols[k], k, gidx, step, a.seed, b0, b1);
+        }
+        float r = point_step<NF, NS, JF>(P, sw, a.params, st, RS, valid, a.inv_n, sink, part);
+        if (a.residual && valid) a.residual[pl] = r;
+    }
+
+    // per-thread scalars -> accumulator
+    {
+        float v = warp_sum(part.loss);
+        if (lane == 0) sink.add(P.n_params, v);
+        v = warp_sum(part.sbar);
+        if (lane == 0) sink.add(P.log_scale_off, v);
+#pragma unroll
+        for (int i = 0; i < PINN_MAX_VARS; ++i) {
+            if (i < P.n_vars) {
+                float t = warp_sum(part.vbar[i]);
+                if (lane == 0) sink.add(P.var_off[i], t);
+            }
+        }
+    }
+    __syncthreads();
+
+    // CTA partial -> global, then the last CTA folds all partials in block order
+    float* mine = a.partials + (size_t)blockIdx.x * n_out_floats;
+    for (int i = tid; i < n_out_floats; i += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < a.n_wacc; ++w) s += wacc_all[w * n_out_floats + i];
+        mine[i] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    if (tid == 0) {
+        unsigned int t = atomicAdd(a.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            int b = 0;
+            const float* src = a.partials + i;
+            for (; b + 3 < (int)gridDim.x; b += 4) {
+                s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
+                s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
+                s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
+                s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
+            }
+            for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
+            a.out[i] = (s0 + s1) + (s2 + s3);
+        }
+        if (tid == 0) *a.ticket = 0u;
+    }
+}
+
+
+typedef void (*StepKernelFn)(const StepArgs);
+
+struct Variant {
+    int nf, ns;
+    StepKernelFn smem_fn, gmem_fn;
+    int maxt;
+};
+
+template <int NF, int NS>
+struct VariantCfg {
+    static constexpr int C = 1 + NF + NS;
+    static constexpr int MAXT = (C <= 3) ? 512 : 256;
+    static constexpr int JF = 16;
+};
+
+template <int NF, int NS>
+static Variant make_variant() {
+    using Cfg = VariantCfg<NF, NS>;
+    Variant v;
+    v.nf = NF; v.ns = NS;
+    v.smem_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF>;
+    v.gmem_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF>;
+    v.maxt = Cfg::MAXT;
+    return v;
+}
+
+}  // namespace pinn
+
+// one lookup function per NF, each defined in its own translation unit
+const pinn::Variant* pinn_variants_nf0(int ns);
+const pinn::Variant* pinn_variants_nf1(int ns);
+const pinn::Variant* pinn_variants_nf2(int ns);
+const pinn::Variant* pinn_variants_nf3(int ns);
+const pinn::Variant* pinn_variants_nf4(int ns);

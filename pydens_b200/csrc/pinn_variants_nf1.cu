@@ -1,0 +1,3 @@
+// step_kernel instantiations for NF = 1 first-order directions (see pinn_variants.inc)
+#define PINN_VARIANT_NF 1
+#include "pinn_variants.inc"

@@ -1,0 +1,663 @@
+""" Symbolic tracing of user `equation` / `initial_condition` callables.
+
+The reference treats the equation as an opaque Python callable executed on autograd tensors every
+iteration (pydens/model_torch.py:448), each `D` being a full reverse sweep (:174-178).  Here the
+callable is run ONCE on symbolic proxies; `D` differentiates symbolically, so the residual becomes
+a small expression DAG over
+
+    x_k (point columns), u, du/dx_i, d2u/dx_i^2, V variables, constants,
+
+from which we derive (a) the derivative jet the network kernel has to carry and (b) two register
+programs (include/pinn_b200.h, PinnInstr): the residual with its partials w.r.t. every jet channel
+and variable, and the jet of the initial condition.  Anything outside this vocabulary raises
+`NotLowerable`; the Solver then uses its autograd path for that problem.
+"""
+import math
+import numbers
+
+import numpy as np
+import torch
+
+
+class NotLowerable(Exception):
+    """ The callable uses something the fused path does not cover. """
+
+
+# ------------------------------------------------------------------------------------------------
+# expression DAG (hash-consed)
+# ------------------------------------------------------------------------------------------------
+UNARY = ('neg', 'sin', 'cos', 'tan', 'exp', 'log', 'sqrt', 'tanh', 'sigmoid', 'abs', 'sign')
+BINARY = ('add', 'sub', 'mul', 'div', 'pow')
+
+
+class Expr:
+    __slots__ = ('kind', 'args', 'value', '_hash')
+    _table = {}
+
+    def __new__(cls, kind, args=(), value=None):
+        key = (kind, tuple(id(a) for a in args), value)
+        hit = cls._table.get(key)
+        if hit is not None:
+            return hit
+        self = object.__new__(cls)
+        self.kind, self.args, self.value = kind, tuple(args), value
+        self._hash = hash(key)
+        cls._table[key] = self
+        return self
+
+    def __hash__(self):
+        return self._hash
+
+    def __eq__(self, other):
+        return self is other
+
+    def __repr__(self):
+        if self.kind == 'const':
+            return repr(self.value)
+        if self.kind == 'coord':
+            return 'x%d' % self.value
+        if self.kind == 'u':
+            return 'u' + ''.join('_%d' % i for i in self.value)
+        if self.kind == 'var':
+            return 'V[%s]' % self.value
+        if self.kind == 'powi':
+            return '(%r)**%d' % (self.args[0], self.value)
+        return '%s(%s)' % (self.kind, ', '.join(map(repr, self.args)))
+
+
+def const(v):
+    v = float(v)
+    if v == 0.0:
+        v = 0.0                      # fold -0.0
+    return Expr('const', (), v)
+
+
+ZERO, ONE = const(0.0), const(1.0)
+
+
+def is_const(e, v=None):
+    return e.kind == 'const' and (v is None or e.value == v)
+
+
+def coord(k):
+    return Expr('coord', (), int(k))
+
+
+def uleaf(multi_index=()):
+    return Expr('u', (), tuple(sorted(multi_index)))
+
+
+def var(name):
+    return Expr('var', (), name)
+
+
+def add(a, b):
+    if is_const(a) and is_const(b):
+        return const(a.value + b.value)
+    if is_const(a, 0.0):
+        return b
+    if is_const(b, 0.0):
+        return a
+    return Expr('add', (a, b))
+
+
+def sub(a, b):
+    if is_const(a) and is_const(b):
+        return const(a.value - b.value)
+    if is_const(b, 0.0):
+        return a
+    if is_const(a, 0.0):
+        return neg(b)
+    if a is b:
+        return ZERO
+    return Expr('sub', (a, b))
+
+
+def neg(a):
+    if is_const(a):
+        return const(-a.value)
+    if a.kind == 'neg':
+        return a.args[0]
+    return Expr('neg', (a,))
+
+
+def mul(a, b):
+    if is_const(a) and is_const(b):
+        return const(a.value * b.value)
+    if is_const(a, 0.0) or is_const(b, 0.0):
+        return ZERO
+    if is_const(a, 1.0):
+        return b
+    if is_const(b, 1.0):
+        return a
+    if is_const(a, -1.0):
+        return neg(b)
+    if is_const(b, -1.0):
+        return neg(a)
+    if is_const(b):                  # constants to the left: canonical form
+        a, b = b, a
+    return Expr('mul', (a, b))
+
+
+def div(a, b):
+    if is_const(b, 1.0):
+        return a
+    if is_const(a) and is_const(b):
+        return const(a.value / b.value)
+    if is_const(a, 0.0):
+        return ZERO
+    return Expr('div', (a, b))
+
+
+def powi(a, n):
+    n = int(n)
+    if n == 0:
+        return ONE
+    if n == 1:
+        return a
+    if is_const(a):
+        return const(a.value ** n)
+    return Expr('powi', (a,), n)
+
+
+def power(a, b):
+    if is_const(b):
+        e = b.value
+        if float(e).is_integer() and abs(e) <= 64:
+            return powi(a, int(e))
+        if e == 0.5:
+            return unary('sqrt', a)
+        if is_const(a):
+            return const(a.value ** e)
+    return Expr('pow', (a, b))
+
+
+_FOLD = {'neg': lambda v: -v, 'sin': math.sin, 'cos': math.cos, 'tan': math.tan, 'exp': math.exp,
+         'log': math.log, 'sqrt': math.sqrt, 'tanh': math.tanh,
+         'sigmoid': lambda v: 1.0 / (1.0 + math.exp(-v)), 'abs': abs,
+         'sign': lambda v: (v > 0) - (v < 0)}
+
+
+def unary(kind, a):
+    if kind == 'neg':
+        return neg(a)
+    if is_const(a):
+        try:
+            return const(_FOLD[kind](a.value))
+        except (ValueError, OverflowError):
+            pass
+    return Expr(kind, (a,))
+
+
+# ------------------------------------------------------------------------------------------------
+# differentiation
+# ------------------------------------------------------------------------------------------------
+def _chain(e, da_of):
+    """ Shared derivative rules; `da_of(arg)` gives the derivative of an argument. """
+    k = e.kind
+    if k in ('add', 'sub'):
+        a, b = e.args
+        return (add if k == 'add' else sub)(da_of(a), da_of(b))
+    if k == 'neg':
+        return neg(da_of(e.args[0]))
+    if k == 'mul':
+        a, b = e.args
+        return add(mul(da_of(a), b), mul(a, da_of(b)))
+    if k == 'div':
+        a, b = e.args
+        da, db = da_of(a), da_of(b)
+        if is_const(db, 0.0):
+            return div(da, b)
+        return sub(div(da, b), mul(div(e, b), db))
+    if k == 'powi':
+        a, n = e.args[0], e.value
+        return mul(mul(const(n), powi(a, n - 1)), da_of(a))
+    if k == 'pow':
+        a, b = e.args
+        da, db = da_of(a), da_of(b)
+        t = ZERO
+        if not is_const(da, 0.0):
+            t = add(t, mul(mul(b, power(a, sub(b, ONE))), da))
+        if not is_const(db, 0.0):
+            t = add(t, mul(mul(e, unary('log', a)), db))
+        return t
+    a = e.args[0]
+    da = da_of(a)
+    if is_const(da, 0.0):
+        return ZERO
+    if k == 'sin':
+        return mul(unary('cos', a), da)
+    if k == 'cos':
+        return neg(mul(unary('sin', a), da))
+    if k == 'tan':
+        return mul(add(ONE, powi(e, 2)), da)
+    if k == 'exp':
+        return mul(e, da)
+    if k == 'log':
+        return div(da, a)
+    if k == 'sqrt':
+        return div(da, mul(const(2.0), e))
+    if k == 'tanh':
+        return mul(sub(ONE, powi(e, 2)), da)
+    if k == 'sigmoid':
+        return mul(mul(e, sub(ONE, e)), da)
+    if k == 'abs':
+        return mul(unary('sign', a), da)
+    if k == 'sign':
+        return ZERO
+    raise NotLowerable('cannot differentiate %r' % k)
+
+
+def diff_coord(e, k, memo=None):
+    """ Total derivative of `e` w.r.t. point column k (u depends on every column). """
+    memo = {} if memo is None else memo
+    hit = memo.get(e)
+    if hit is not None:
+        return hit
+    if e.kind == 'const' or e.kind == 'var':
+        r = ZERO
+    elif e.kind == 'coord':
+        r = ONE if e.value == k else ZERO
+    elif e.kind == 'u':
+        if len(e.value) >= 2:
+            raise NotLowerable('derivatives of order > 2 are not supported by the fused path')
+        r = uleaf(e.value + (k,))
+    else:
+        r = _chain(e, lambda a: diff_coord(a, k, memo))
+    memo[e] = r
+    return r
+
+
+def diff_leaf(e, leaf, memo=None):
+    """ Partial derivative of `e` w.r.t. one leaf (a jet channel of u or a variable). """
+    memo = {} if memo is None else memo
+    hit = memo.get(e)
+    if hit is not None:
+        return hit
+    if e is leaf:
+        r = ONE
+    elif e.kind in ('const', 'coord', 'u', 'var'):
+        r = ZERO
+    else:
+        r = _chain(e, lambda a: diff_leaf(a, leaf, memo))
+    memo[e] = r
+    return r
+
+
+def leaves(e, kinds, seen=None, out=None):
+    seen = set() if seen is None else seen
+    out = [] if out is None else out
+    if e in seen:
+        return out
+    seen.add(e)
+    if e.kind in kinds:
+        out.append(e)
+    for a in e.args:
+        leaves(a, kinds, seen, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# proxies handed to user callables
+# ------------------------------------------------------------------------------------------------
+def _as_expr(x):
+    if isinstance(x, Sym):
+        return x.expr
+    if isinstance(x, (numbers.Real, np.floating, np.integer)):
+        return const(float(x))
+    if isinstance(x, np.ndarray) and x.size == 1:
+        return const(float(x.reshape(-1)[0]))
+    if isinstance(x, torch.Tensor):
+        if x.numel() == 1 and not x.requires_grad:
+            return const(float(x.reshape(-1)[0]))
+        raise NotLowerable('tensor constants with more than one element (or requiring grad) in the equation')
+    raise NotLowerable('unsupported operand of type %s' % type(x).__name__)
+
+
+_TORCH_UNARY = {'sin': 'sin', 'cos': 'cos', 'tan': 'tan', 'exp': 'exp', 'log': 'log', 'sqrt': 'sqrt',
+                'tanh': 'tanh', 'sigmoid': 'sigmoid', 'abs': 'abs', 'absolute': 'abs', 'neg': 'neg',
+                'negative': 'neg', 'sign': 'sign'}
+_TORCH_BINARY = {'add': add, 'sub': sub, 'subtract': sub, 'mul': mul, 'multiply': mul, 'div': div,
+                 'divide': div, 'true_divide': div, 'pow': power}
+_NP_UNARY = {np.sin: 'sin', np.cos: 'cos', np.tan: 'tan', np.exp: 'exp', np.log: 'log', np.sqrt: 'sqrt',
+             np.tanh: 'tanh', np.abs: 'abs', np.negative: 'neg', np.sign: 'sign'}
+_NP_BINARY = {np.add: add, np.subtract: sub, np.multiply: mul, np.divide: div, np.true_divide: div,
+              np.power: power}
+
+
+class Sym:
+    """ Symbolic stand-in for an `[N, 1]` tensor inside a traced callable. """
+    __array_priority__ = 1000
+
+    def __init__(self, expr):
+        self.expr = expr
+
+    # arithmetic
+    def __add__(self, o): return Sym(add(self.expr, _as_expr(o)))
+    def __radd__(self, o): return Sym(add(_as_expr(o), self.expr))
+    def __sub__(self, o): return Sym(sub(self.expr, _as_expr(o)))
+    def __rsub__(self, o): return Sym(sub(_as_expr(o), self.expr))
+    def __mul__(self, o): return Sym(mul(self.expr, _as_expr(o)))
+    def __rmul__(self, o): return Sym(mul(_as_expr(o), self.expr))
+    def __truediv__(self, o): return Sym(div(self.expr, _as_expr(o)))
+    def __rtruediv__(self, o): return Sym(div(_as_expr(o), self.expr))
+    def __pow__(self, o): return Sym(power(self.expr, _as_expr(o)))
+    def __rpow__(self, o): return Sym(power(_as_expr(o), self.expr))
+    def __neg__(self): return Sym(neg(self.expr))
+    def __pos__(self): return self
+    def __abs__(self): return Sym(unary('abs', self.expr))
+
+    # tensor-ish methods users reach for
+    def sin(self): return Sym(unary('sin', self.expr))
+    def cos(self): return Sym(unary('cos', self.expr))
+    def exp(self): return Sym(unary('exp', self.expr))
+    def log(self): return Sym(unary('log', self.expr))
+    def sqrt(self): return Sym(unary('sqrt', self.expr))
+    def tanh(self): return Sym(unary('tanh', self.expr))
+    def abs(self): return Sym(unary('abs', self.expr))
+    def pow(self, o): return self.__pow__(o)
+    def square(self): return Sym(powi(self.expr, 2))
+    def view(self, *shape): return self
+    def reshape(self, *shape): return self
+    def float(self): return self
+
+    def __bool__(self):
+        raise NotLowerable('data-dependent control flow in a traced callable')
+
+    def _compare(self, other):
+        raise NotLowerable('comparisons (data-dependent control flow) in a traced callable')
+
+    __lt__ = __le__ = __gt__ = __ge__ = _compare
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        raise NotLowerable('tensor attribute %r is not available while tracing' % name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        name = getattr(func, '__name__', None)
+        if kwargs:
+            raise NotLowerable('keyword arguments to torch.%s while tracing' % name)
+        if name in ('__add__', '__radd__'): name = 'add'
+        if name in ('__mul__', '__rmul__'): name = 'mul'
+        if name in ('__sub__',): name = 'sub'
+        if name in ('__truediv__',): name = 'div'
+        if name in ('__pow__',): name = 'pow'
+        if name == '__rsub__':
+            return Sym(sub(_as_expr(args[1]), _as_expr(args[0])))
+        if name == '__rtruediv__':
+            return Sym(div(_as_expr(args[1]), _as_expr(args[0])))
+        if name == '__rpow__':
+            return Sym(power(_as_expr(args[1]), _as_expr(args[0])))
+        if name in _TORCH_UNARY and len(args) == 1:
+            return Sym(unary(_TORCH_UNARY[name], _as_expr(args[0])))
+        if name in _TORCH_BINARY and len(args) == 2:
+            return Sym(_TORCH_BINARY[name](_as_expr(args[0]), _as_expr(args[1])))
+        if name == 'square' and len(args) == 1:
+            return Sym(powi(_as_expr(args[0]), 2))
+        if name == 'reciprocal' and len(args) == 1:
+            return Sym(div(ONE, _as_expr(args[0])))
+        if name in ('zeros_like', 'ones_like') and len(args) == 1:
+            return Sym(ZERO if name == 'zeros_like' else ONE)
+        raise NotLowerable('torch.%s is not supported by the fused path' % name)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or kwargs:
+            raise NotLowerable('numpy ufunc %s.%s while tracing' % (ufunc.__name__, method))
+        if ufunc in _NP_UNARY and len(inputs) == 1:
+            return Sym(unary(_NP_UNARY[ufunc], _as_expr(inputs[0])))
+        if ufunc in _NP_BINARY and len(inputs) == 2:
+            return Sym(_NP_BINARY[ufunc](_as_expr(inputs[0]), _as_expr(inputs[1])))
+        if ufunc is np.square:
+            return Sym(powi(_as_expr(inputs[0]), 2))
+        raise NotLowerable('numpy.%s is not supported by the fused path' % ufunc.__name__)
+
+
+def sym_D(y, x):
+    """ Symbolic counterpart of the D token. """
+    if not isinstance(x, Sym) or x.expr.kind != 'coord':
+        raise NotLowerable('D(y, x): x must be one of the equation arguments')
+    return Sym(diff_coord(_as_expr(y), x.expr.value))
+
+
+# ------------------------------------------------------------------------------------------------
+# lowering: expression DAGs -> register programs
+# ------------------------------------------------------------------------------------------------
+OP = dict(CONST=0, COORD=1, VAR=2, ADD=3, SUB=4, MUL=5, DIV=6, NEG=7, MULI=8, ADDI=9, SIN=10, COS=11,
+          EXP=12, LOG=13, SQRT=14, TANH=15, POWI=16, POW=17, ABS=18, SIGN=19, SIGMOID=20, RECIP=21, TAN=22)
+_UNARY_OP = {'neg': 'NEG', 'sin': 'SIN', 'cos': 'COS', 'tan': 'TAN', 'exp': 'EXP', 'log': 'LOG',
+             'sqrt': 'SQRT', 'tanh': 'TANH', 'sigmoid': 'SIGMOID', 'abs': 'ABS', 'sign': 'SIGN'}
+MAX_PROG, MAX_SLOTS = 192, 96
+
+
+class Program:
+    """ instrs: list of (op, dst, a, b, imm); outs: slot of every requested output. """
+
+    def __init__(self, instrs, outs, n_slots):
+        self.instrs, self.outs, self.n_slots = instrs, outs, n_slots
+
+    def __len__(self):
+        return len(self.instrs)
+
+
+def lower(outputs, channel_of_u, var_index, n_reserved):
+    """ Linearise `outputs` (list of Expr) into one program.
+
+    Slots [0, n_reserved) hold the jet of u on entry and are never written; `channel_of_u` maps a
+    'u' leaf to its reserved slot; `var_index` maps a variable name to its VAR operand.
+    """
+    order, seen = [], set()
+
+    def visit(e):
+        if e in seen:
+            return
+        seen.add(e)
+        for a in e.args:
+            visit(a)
+        order.append(e)
+
+    for o in outputs:
+        visit(o)
+
+    def immediate_form(e):
+        """ (op, operand, imm) when a binary node has a constant side that fits an immediate. """
+        if e.kind == 'add':
+            a, b = e.args
+            if is_const(b): return 'ADDI', a, b.value
+            if is_const(a): return 'ADDI', b, a.value
+        if e.kind == 'sub' and is_const(e.args[1]):
+            return 'ADDI', e.args[0], -e.args[1].value
+        if e.kind == 'mul':
+            a, b = e.args
+            if is_const(a): return 'MULI', b, a.value
+            if is_const(b): return 'MULI', a, b.value
+        return None
+
+    # which nodes need a materialised value (constants folded into immediates do not)
+    needed = set()
+    for e in order:
+        imm = immediate_form(e)
+        if imm:
+            needed.add(imm[1])
+        else:
+            needed.update(e.args)
+    needed.update(outputs)
+
+    last_use = {}
+    for i, e in enumerate(order):
+        imm = immediate_form(e)
+        for a in ([imm[1]] if imm else e.args):
+            last_use[a] = i
+    for o in outputs:
+        last_use[o] = len(order) + 1          # outputs stay live
+
+    slot_of, free, next_slot = {}, [], [n_reserved]
+    instrs = []
+
+    def alloc():
+        if free:
+            free.sort()
+            return free.pop(0)
+        s = next_slot[0]
+        next_slot[0] += 1
+        if s >= MAX_SLOTS:
+            raise NotLowerable('expression needs more than %d scratch slots' % MAX_SLOTS)
+        return s
+
+    for i, e in enumerate(order):
+        if e not in needed:
+            continue
+        if e.kind == 'u':
+            if e not in channel_of_u:
+                raise NotLowerable('unexpected derivative leaf %r' % e)
+            slot_of[e] = channel_of_u[e]
+            continue
+        imm = immediate_form(e)
+        operands = [imm[1]] if imm else list(e.args)
+        srcs = [slot_of[a] for a in operands]
+        # operands whose last use is this instruction free their slot (never a reserved/output one)
+        for a in operands:
+            if last_use.get(a) == i and a.kind != 'u' and slot_of[a] >= n_reserved and slot_of[a] not in free:
+                free.append(slot_of[a])
+        dst = alloc()
+        slot_of[e] = dst
+        if e.kind == 'const':
+            instrs.append((OP['CONST'], dst, 0, 0, e.value))
+        elif e.kind == 'coord':
+            instrs.append((OP['COORD'], dst, e.value, 0, 0.0))
+        elif e.kind == 'var':
+            if e.value not in var_index:
+                raise NotLowerable('variable %r is not available here' % e.value)
+            instrs.append((OP['VAR'], dst, var_index[e.value], 0, 0.0))
+        elif imm:
+            instrs.append((OP[imm[0]], dst, srcs[0], 0, imm[2]))
+        elif e.kind in ('add', 'sub', 'mul', 'div', 'pow'):
+            instrs.append((OP[e.kind.upper()], dst, srcs[0], srcs[1], 0.0))
+        elif e.kind == 'powi':
+            instrs.append((OP['POWI'], dst, srcs[0], 0, float(e.value)))
+        elif e.kind in _UNARY_OP:
+            instrs.append((OP[_UNARY_OP[e.kind]], dst, srcs[0], 0, 0.0))
+        else:
+            raise NotLowerable('cannot lower %r' % e.kind)
+    if len(instrs) > MAX_PROG:
+        raise NotLowerable('expression needs %d instructions (max %d)' % (len(instrs), MAX_PROG))
+    return Program(instrs, [slot_of[o] for o in outputs], max(next_slot[0], n_reserved))
+
+
+def run_program(prog, ujet, coords, var_values):
+    """ Reference interpreter of a Program on numpy arrays (host-side check of the lowering).
+    ujet: [C, N] values of the reserved slots; coords: [total, N]; returns the list of outputs. """
+    n = coords.shape[1]
+    slots = np.zeros((max(prog.n_slots, 1), n), dtype=coords.dtype)
+    slots[:ujet.shape[0]] = ujet
+    inv = {v: k for k, v in OP.items()}
+    for op, dst, a, b, imm in prog.instrs:
+        name = inv[op]
+        if name == 'CONST': r = np.full(n, imm, dtype=coords.dtype)
+        elif name == 'COORD': r = coords[a]
+        elif name == 'VAR': r = np.full(n, var_values[a], dtype=coords.dtype)
+        elif name == 'ADD': r = slots[a] + slots[b]
+        elif name == 'SUB': r = slots[a] - slots[b]
+        elif name == 'MUL': r = slots[a] * slots[b]
+        elif name == 'DIV': r = slots[a] / slots[b]
+        elif name == 'POW': r = np.power(slots[a], slots[b])
+        elif name == 'NEG': r = -slots[a]
+        elif name == 'MULI': r = slots[a] * coords.dtype.type(imm)
+        elif name == 'ADDI': r = slots[a] + coords.dtype.type(imm)
+        elif name == 'POWI': r = slots[a] ** int(imm)
+        elif name == 'SIGMOID': r = 1.0 / (1.0 + np.exp(-slots[a]))
+        elif name == 'RECIP': r = 1.0 / slots[a]
+        else: r = getattr(np, {'ABS': 'abs'}.get(name, name.lower()))(slots[a])
+        slots[dst] = r
+    return [slots[s].copy() for s in prog.outs]
+
+
+# ------------------------------------------------------------------------------------------------
+# tracing entry points
+# ------------------------------------------------------------------------------------------------
+class TracedEquation:
+    """ Result of tracing: jet set + residual program (+ IC program). """
+
+    def __init__(self):
+        self.residual = None        # Expr
+        self.dirs = []              # point columns of the first-order directions (second-order first)
+        self.ns = 0                 # how many of them also carry a second derivative
+        self.var_names = []         # variables used by the equation, in VAR-operand order
+        self.eq_prog = None         # outputs: [r, dr/dchannel_0 .. dr/dchannel_{C-1}, dr/dV_0 ..]
+        self.ic_prog = None         # outputs: jet of ic (C entries) or None
+        self.n_slots = 0
+
+    @property
+    def nf(self):
+        return len(self.dirs)
+
+    @property
+    def channels(self):
+        return 1 + self.nf + self.ns
+
+
+def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0, run=None):
+    """ Trace `equation(u, *xs)` (and `initial_condition(*x_spatial)` if callable).
+
+    `var_factory(name)` is installed by the caller so that V(name, ...) returns `Sym(var(name))`
+    during the trace.  `run` wraps the call (the Solver passes its contextvars ctx.run).
+    """
+    run = run or (lambda f, *a: f(*a))
+    xs = [Sym(coord(k)) for k in range(total)]
+    out = run(equation, Sym(uleaf()), *xs)
+    if not isinstance(out, Sym):
+        out = Sym(_as_expr(out))
+    res = out.expr
+    T = TracedEquation()
+    T.residual = res
+
+    u_leaves = leaves(res, ('u',))
+    first, second = set(), set()
+    for l in u_leaves:
+        mi = l.value
+        if len(mi) == 1:
+            first.add(mi[0])
+        elif len(mi) == 2:
+            if mi[0] != mi[1]:
+                raise NotLowerable('mixed second derivatives are not supported by the fused path yet')
+            second.add(mi[0]); first.add(mi[0])
+    T.dirs = sorted(second) + sorted(first - second)
+    T.ns = len(second)
+    nf, ns = len(T.dirs), T.ns
+    if nf > 4:
+        raise NotLowerable('more than 4 derivative directions')
+    C = 1 + nf + ns
+    chan = {uleaf(): 0}
+    for d, col in enumerate(T.dirs):
+        chan[uleaf((col,))] = 1 + d
+        if d < ns:
+            chan[uleaf((col, col))] = 1 + nf + d
+    by_channel = {v: k for k, v in chan.items()}
+
+    T.var_names = sorted({l.value for l in leaves(res, ('var',))})
+    if len(T.var_names) > 4:
+        raise NotLowerable('more than 4 trainable variables in the equation')
+    var_index = {n: i for i, n in enumerate(T.var_names)}
+
+    outputs = [res] + [diff_leaf(res, by_channel[c]) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
+    T.eq_prog = lower(outputs, chan, var_index, C)
+    T.n_slots = T.eq_prog.n_slots
+
+    if initial_condition is not None:
+        if callable(initial_condition):
+            ic_out = run(initial_condition, *xs[:ndims_spatial])
+            ic = ic_out.expr if isinstance(ic_out, Sym) else _as_expr(ic_out)
+        else:
+            ic = const(float(np.float32(initial_condition)))
+        if leaves(ic, ('var',)):
+            raise NotLowerable('V variables inside initial_condition are not supported by the fused path yet')
+        if leaves(ic, ('u',)):
+            raise NotLowerable('initial_condition must not depend on the solution')
+        jet = [ic]
+        firsts = [diff_coord(ic, col) for col in T.dirs]
+        jet += firsts
+        jet += [diff_coord(firsts[d], T.dirs[d]) for d in range(ns)]
+        T.ic_prog = lower(jet, {}, {}, C)
+        T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
+    return T

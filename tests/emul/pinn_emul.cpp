@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY — host emulation of the per-point device code.
+//
+// Compiles pydens_b200/csrc/pinn_device.cuh (the very functions the CUDA kernel runs per thread)
+// with g++ and drives them one point at a time, so the forward jets, ansatz, residual programs and
+// the hand-derived reverse sweep can be checked against the oracle on a machine without a GPU.
+// The warp-level gradient reduction is replaced by direct accumulation (emit_entries' host branch).
+// Never loaded by the product (pydens_b200/_native.py loads only libpinn_b200.so).
+#include <vector>
+#include <string.h>
+#include "../../pydens_b200/csrc/pinn_host_plan.h"
+
+using namespace pinn;
+
+template <int NF, int NS>
+static void run_step(const DevPlan& P, const float* sw, const float* params, const float* points, long long n,
+                     float inv_n, float* out, float* residual) {
+    std::vector<float> st(P.rows_total, 0.0f);
+    GradSink sink;
+    sink.wacc = out;
+    sink.atomic = false;
+    PointPartials<NF, NS> part;
+    part.loss = 0.0f; part.sbar = 0.0f;
+    for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
+    for (long long p = 0; p < n; ++p) {
+        for (int k = 0; k < P.total; ++k) st[k] = points[p * P.total + k];
+        float r = point_step<NF, NS, 16>(P, sw, params, st.data(), 1, true, inv_n, sink, part);
+        if (residual) residual[p] = r;
+    }
+    out[P.n_params] += part.loss;
+    out[P.log_scale_off] += part.sbar;
+    for (int i = 0; i < P.n_vars; ++i) out[P.var_off[i]] += part.vbar[i];
+}
+
+extern "C" int emul_step(const PinnSpec* spec, const float* params, const float* points, long long n, float inv_n,
+                         float* out, float* residual, char* msg, int msg_len) {
+    DevPlan P;
+    int fr, fs;
+    int rc = build_dev_plan(spec, P, fr, fs, msg, (size_t)msg_len);
+    if (rc) return rc;
+    std::vector<float> sw(P.weights_floats + 16);
+    host_stage_weights(P, params, sw.data());
+    for (int i = 0; i < P.n_params + 4; ++i) out[i] = 0.0f;
+#define CASE(NF_, NS_) if (P.nf == NF_ && P.ns == NS_) { run_step<NF_, NS_>(P, sw.data(), params, points, n, inv_n, out, residual); return 0; }
+    CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2)
+    CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
+    CASE(4, 0) CASE(4, 1) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+#undef CASE
+    snprintf(msg, msg_len, "no variant nf=%d ns=%d", P.nf, P.ns);
+    return PINN_E_UNSUPPORTED;
+}
+
+extern "C" int emul_forward(const PinnSpec* spec, const float* params, const float* points, long long n,
+                            float* u_out, char* msg, int msg_len) {
+    DevPlan P;
+    int fwd_rows, fwd_row_scr;
+    int rc = build_dev_plan(spec, P, fwd_rows, fwd_row_scr, msg, (size_t)msg_len);
+    if (rc) return rc;
+    std::vector<float> sw(P.weights_floats + 16);
+    host_stage_weights(P, params, sw.data());
+    std::vector<float> st(fwd_rows, 0.0f);
+    for (long long p = 0; p < n; ++p) {
+        for (int k = 0; k < P.total; ++k) st[k] = points[p * P.total + k];
+        u_out[p] = point_forward<16>(P, sw.data(), params, st.data(), 1, fwd_row_scr);
+    }
+    return 0;
+}
+
+// Philox / sampler restatement check: same code path as sample_kernel.
+extern "C" void emul_sample(const PinnColumn* cols, int total, unsigned long long seed, unsigned long long step,
+                            unsigned long long point_offset, long long n, float* out) {
+    for (long long p = 0; p < n; ++p) {
+        const uint64_t gidx = point_offset + (uint64_t)p;
+        const uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16);
+        Philox4 b0 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3, (uint32_t)seed,
+                                   (uint32_t)(seed >> 32));
+        Philox4 b1 = b0;
+        if (total > 4)
+            b1 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3 | 1u, (uint32_t)seed,
+                               (uint32_t)(seed >> 32));
+        for (int k = 0; k < total; ++k) out[p * total + k] = sample_column(cols[k], k, gidx, step, seed, b0, b1);
+    }
+}

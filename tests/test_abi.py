@@ -1,0 +1,53 @@
+""" The C-ABI library loads and exports every symbol include/pinn_b200.h declares (no compute calls:
+runs without a GPU), and the ctypes mirror of PinnSpec matches the C layout. """
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from pydens_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'pinn_b200.h')
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(pinn_[a-z_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = declared_functions()
+    assert len(names) >= 11
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_native.EXPORTS)
+    assert lib.pinn_abi_version() == _native.ABI_VERSION
+
+
+def test_struct_layout_matches_c(tmp_path):
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pinn_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PinnSpec), sizeof(PinnInstr),'
+                   ' sizeof(PinnColumn), sizeof(PinnPlanInfo), offsetof(PinnSpec, eq_prog), offsetof(PinnSpec, ic_out),'
+                   ' offsetof(PinnSpec, n_slots));return 0;}\n')
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = list(map(int, subprocess.check_output([str(exe)]).split()))
+    S = _native.PinnSpec
+    assert got == [C.sizeof(S), C.sizeof(_native.PinnInstr), C.sizeof(_native.PinnColumn),
+                   C.sizeof(_native.PinnPlanInfo), S.eq_prog.offset, S.ic_out.offset, S.n_slots.offset]
+
+
+def test_plan_create_rejects_bad_spec_without_gpu():
+    lib = _native.load()
+    spec = _native.PinnSpec()
+    spec.abi_version = 999
+    plan = C.c_void_p()
+    rc = lib.pinn_plan_create(C.byref(spec), 0, C.byref(plan))
+    assert rc == _native.E_INVALID
+    assert b'abi_version' in lib.pinn_last_error()

@@ -1,0 +1,104 @@
+""" Host-side logic of the pydens API on CPU (autograd path): signatures, reshape_and_concat contract,
+V / constraints / freeze semantics, lowering decisions.  The fused path itself is exercised with
+-m gpu (test_gpu_parity.py, test_gpu_fit.py). """
+import numpy as np
+import pytest
+import torch
+
+import pydens
+from pydens import Solver, D, V, NumpySampler, ConvBlockModel, TorchModel
+
+
+def pde(f, x, y):
+    return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
+
+
+def test_import_surface_matches_reference():
+    for name in ('Solver', 'D', 'V', 'TorchModel', 'ConvBlockModel', 'NumpySampler'):
+        assert hasattr(pydens, name)
+    assert pydens.__version__.startswith('1.0.2')
+
+
+def test_readme_poisson_on_cpu_autograd_path():
+    torch.manual_seed(0)
+    solver = Solver(equation=pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh',
+                    units=[10, 12, 15, 1], device='cpu')
+    assert solver._traced is not None and solver._traced.dirs == [0, 1] and solver._traced.ns == 2
+    assert sum(p.numel() for p in solver.model.conv_block.parameters()) == 373
+    solver.fit(batch_size=100, niters=30)
+    assert len(solver.losses) == 30 and isinstance(solver.losses[0], np.ndarray) and solver.losses[0].shape == ()
+    solver.fit(batch_size=50, niters=5, optimizer=None)          # re-uses the optimizer, list keeps growing
+    assert len(solver.losses) == 35
+    grid = np.linspace(0, 1, 7)
+    out = solver.predict(grid, 0.0)                               # boundary y=0 -> bc value exactly
+    assert out.shape == (7, 1) and np.allclose(out, 1.0)
+
+
+def test_fused_backend_raises_without_gpu_or_lowering():
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    solver = Solver(pde, ndims=2, boundary_condition=1, device='cpu', backend='fused')
+    with pytest.raises(RuntimeError):
+        solver.fit(niters=1, batch_size=10)
+    with pytest.raises(RuntimeError):
+        Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu', backend='fused')
+
+
+def test_reshape_and_concat_contract():
+    rc = Solver.reshape_and_concat
+    out = rc([np.linspace(0, 1, 5), 2, [1., 2., 3., 4., 5.], torch.arange(5.)])
+    assert out.shape == (5, 4) and out.dtype == torch.float32
+    assert torch.all(out[:, 1] == 2)
+    assert rc([0.5, 1]).shape == (1, 2)
+    assert torch.equal(rc([np.array([[3.0], [4.0]]), np.array([7.0, 8.0, 9.0])[:1].repeat(2)])[:, 0],
+                       torch.tensor([3.0, 4.0]))
+    short = rc([np.arange(6.0), np.array([9.0, 10.0])])           # wrong-sized array: first element tiled
+    assert torch.all(short[:, 1] == 9.0)
+
+
+def test_variables_constraints_and_freezing():
+    def odevar(f, x):
+        return D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x) + V('new_var', data=torch.Tensor([1.0]))
+    torch.manual_seed(1)
+    solver = Solver(odevar, ndims=1, initial_condition=1, constraints=lambda f, x: f(torch.tensor([0.5])),
+                    device='cpu')
+    assert isinstance(solver.model.new_var, torch.nn.Parameter)
+    assert solver._traced.var_names == ['new_var']
+    solver.model.freeze_trainable(variables=('new_var',))
+    solver.fit(niters=5, batch_size=20, lr=0.1)
+    assert float(solver.model.new_var) == 1.0
+    solver.model.unfreeze_trainable(variables=['new_var'])
+    solver.fit(niters=5, batch_size=20, lr=0.1, loss_terms=['equation', 'constraint_0'])
+    assert float(solver.model.new_var) != 1.0
+    solver.model.freeze_layers(['fc1'], ['log_scale'])            # README spelling
+    assert not solver.model.conv_block.linears[0].weight.requires_grad
+    assert not solver.model.log_scale.requires_grad
+
+
+def test_lowering_decisions():
+    assert Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu')._traced is None
+    s = Solver(lambda f, x, y: D(D(f, x), y), ndims=2, device='cpu')
+    assert s._traced is None and 'mixed' in s._lower_error
+    s = Solver(lambda f, t: D(f, t), ndims=1, initial_condition=lambda: V('init', data=torch.Tensor([3.0])),
+               device='cpu')
+    assert s._traced is None                                      # V inside the initial condition
+    s.fit(niters=2, batch_size=8)                                 # … still trains on the autograd path
+    s = Solver(pde, ndims=2, layout='faR fa+ f', features=[6, 6, 1], device='cpu')
+    assert s._traced is None and 'dense chain' in s._lower_error
+    s.fit(niters=2, batch_size=8)
+
+    class MyModel(ConvBlockModel):
+        def forward(self, xs):
+            return super().forward(xs) * 2
+    assert Solver(pde, ndims=2, model=MyModel, device='cpu')._traced is None
+
+
+def test_sampler_and_domain_handling():
+    s = Solver(lambda f, x, e: D(f, x) - e * np.pi * torch.cos(e * np.pi * x), ndims=1, nparams=1,
+               initial_condition=2.0, device='cpu')
+    s.fit(niters=3, batch_size=16, sampler=NumpySampler('u') & NumpySampler('u', low=.5, high=5.5), lr=0.01)
+    assert np.allclose(s.predict(0.0, 3.0), 2.0)                  # t = t0 -> initial condition
+    with pytest.raises(ValueError):
+        Solver(pde, ndims=2, domain=3, device='cpu')
+    s2 = Solver(pde, ndims=2, domain=[(-1, 1), (0, 2)], boundary_condition=0.5, device='cpu')
+    assert np.allclose(s2.predict(-1.0, 1.0), 0.5)

@@ -1,0 +1,59 @@
+""" The per-thread device code (pydens_b200/csrc/pinn_device.cuh), compiled for the host by
+tests/emul, against the reference goldens and the fp64 oracle.  CPU only: this is how the kernel's
+math is checked before it ever reaches a GPU.  (The GPU parity tests are in test_gpu_parity.py.) """
+import numpy as np
+import pytest
+import torch
+
+import problems as P
+import emul_harness as E
+from helpers import load_golden, oracle_problem, rel_l2
+
+
+@pytest.mark.parametrize('name', list(P.PROBLEMS))
+def test_device_math_matches_reference(name):
+    g = load_golden(name)
+    spec = E.spec_for(name)
+    assert spec.n_params == g['params'].size
+    loss, residual, grads = E.emul_step(spec, g['params'], g['points'])
+    assert abs(loss - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))          # fp32 tolerance
+    assert rel_l2(residual, g['residual']) <= 1e-5
+    assert rel_l2(grads, g['grads']) <= 1e-4
+    u = E.emul_forward(spec, g['params'], g['points'])
+    assert rel_l2(u, g['u']) <= 1e-5
+
+
+@pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var'])
+def test_device_math_vs_fp64(name):
+    g = load_golden(name)
+    spec = E.spec_for(name)
+    _, _, grads = E.emul_step(spec, g['params'], g['points'])
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    _, _, g64 = prob.loss_and_grads(g['points'].astype(np.float64))
+    ours, ref = rel_l2(grads, g64.numpy()), rel_l2(g['grads'], g64.numpy())
+    assert ours <= max(4 * ref, 5e-6)           # no worse than the reference's own fp32 error
+
+
+def test_per_tensor_gradients_poisson():
+    """ SURVEY 8c tolerance: per-tensor gradient rel-L2 <= 1e-4. """
+    g = load_golden('poisson2d')
+    spec = E.spec_for('poisson2d')
+    _, _, grads = E.emul_step(spec, g['params'], g['points'])
+    for l in range(spec.n_layers):
+        n_in, n_out = spec.widths[l], spec.widths[l + 1]
+        w = slice(spec.w_off[l], spec.w_off[l] + n_in * n_out)
+        b = slice(spec.b_off[l], spec.b_off[l] + n_out)
+        assert rel_l2(grads[w], g['grads'][w]) <= 1e-4
+        assert rel_l2(grads[b], g['grads'][b]) <= 1e-4
+
+
+def test_ragged_and_single_point():
+    g = load_golden('burgers')
+    spec = E.spec_for('burgers')
+    prob = oracle_problem('burgers', torch.float32, g['params'])
+    for n in (1, 31, 33):
+        pts = g['points'][:n]
+        loss, res, grads = E.emul_step(spec, g['params'], pts)
+        l, r, gr = prob.loss_and_grads(pts)
+        assert abs(loss - l) <= 1e-5 * abs(l)
+        assert rel_l2(grads, gr.numpy()) <= 1e-4

@@ -1,0 +1,120 @@
+""" Solver.fit on the fused path (GPU): trajectories against the reference's own fit (goldens),
+CUDA-graph replay == plain launches, in-kernel samplers, constraints hybrid, tutorial flows. """
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import problems as P
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gpu_helpers import make_solver, Replay
+    from pydens_b200 import Solver, D, V, NumpySampler
+
+
+@pytest.mark.parametrize('name', list(P.GOLDEN_TRAJ))
+def test_fit_trajectory_matches_reference_fit(name):
+    """ Same init, same point stream, same Adam: the loss curve of the fused fit follows the curve of the
+    reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points). """
+    g = load_golden(name)
+    niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
+    solver = make_solver(name, g['params'])
+    batches = [P.make_points(name, batch, seed=1000 + i) for i in range(niters)]
+    solver.fit(niters=niters, batch_size=batch, sampler=Replay(batches), lr=lr)
+    losses = np.asarray(solver.losses, dtype=np.float64)
+    ref = g['traj_losses'].astype(np.float64)
+    assert losses.shape == ref.shape
+    assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-3
+    assert abs(losses[-1] - ref[-1]) <= 1e-5 * max(1.0, abs(ref[-1]))
+    final = solver.flat_params().cpu().numpy()
+    assert np.linalg.norm(final - g['traj_params']) / np.linalg.norm(g['traj_params']) <= 1e-3
+
+
+def test_graph_replay_equals_plain_launches():
+    g = load_golden('poisson2d')
+    curves = []
+    for no_graph in ('0', '1'):
+        os.environ['PYDENS_B200_NO_GRAPH'] = no_graph
+        try:
+            solver = make_solver('poisson2d', g['params'])
+            solver.fit(niters=40, batch_size=5000, lr=0.005)
+        finally:
+            os.environ.pop('PYDENS_B200_NO_GRAPH', None)
+        curves.append(np.asarray(solver.losses, dtype=np.float64))
+    assert len(curves[0]) == 40 and np.isfinite(curves[0]).all()
+    np.testing.assert_allclose(curves[0], curves[1], rtol=1e-6)
+    assert curves[0][-1] < curves[0][0]
+
+
+def test_readme_examples_train():
+    def pde(f, x, y):
+        return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
+    torch.manual_seed(0)
+    solver = Solver(equation=pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh',
+                    units=[10, 12, 15, 1])
+    solver.fit(batch_size=100, niters=1500)
+    assert len(solver.losses) == 1500 and solver._engine is not None
+    assert np.mean(solver.losses[-50:]) < 0.1 * np.mean(solver.losses[:10])
+
+    def odeparam(f, x, e):
+        return D(f, x) - e * np.pi * torch.cos(e * np.pi * x)
+    s = NumpySampler('uniform') & NumpySampler('uniform', low=1, high=5)
+    solver = Solver(equation=odeparam, ndims=1, nparams=1, initial_condition=1)
+    solver.fit(batch_size=1000, sampler=s, niters=2000, lr=0.01)
+    assert np.mean(solver.losses[-50:]) < 0.2 * np.mean(solver.losses[:10])
+    xs = np.linspace(0, 1, 50)
+    approx = solver.predict(xs, 2.0).reshape(-1)
+    assert np.abs(approx - (np.sin(2.0 * np.pi * xs) + 1)).max() < 0.5
+
+
+def test_tutorial_ode_accuracy():
+    """ tutorial problem 1: u' = 2 pi cos(2 pi x), u(0) = .5 -> sin(2 pi x) + .5 """
+    torch.manual_seed(0)
+    solver = Solver(lambda f, x: D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x), ndims=1, initial_condition=.5,
+                    activation='Tanh', layout='fafaf', features=[12, 10, 1])
+    solver.fit(niters=1500, batch_size=400, lr=0.02)
+    xs = np.linspace(0, 1, 100)
+    err = np.abs(solver.predict(xs).reshape(-1) - (np.sin(2 * np.pi * xs) + .5)).max()
+    assert err < 0.1
+
+
+def test_variable_constraint_hybrid():
+    def odevar(f, x):
+        return D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x) + V('new_var', data=torch.Tensor([1.0]))
+    torch.manual_seed(0)
+    solver = Solver(odevar, ndims=1, initial_condition=1, constraints=lambda f, x: f(torch.tensor([0.5])))
+    solver.model.freeze_trainable(variables=('new_var',))
+    solver.fit(niters=200, batch_size=500, lr=0.1)
+    assert float(solver.model.new_var.detach()) == 1.0 and solver._engine is not None
+    solver.model.unfreeze_trainable(variables=['new_var'])
+    solver.fit(niters=100, batch_size=100, lr=0.1, loss_terms=['equation', 'constraint_0'])
+    assert float(solver.model.new_var.detach()) != 1.0
+    assert len(solver.losses) == 300 and np.isfinite(solver.losses).all()
+
+
+def test_autograd_path_on_gpu_matches_fused_step():
+    """ backend='torch' (device-aware restatement of the reference loop) and the fused kernel agree. """
+    g = load_golden('heat_param')
+    fused = make_solver('heat_param', g['params'])
+    loss, grads, _ = fused.loss_and_grads(g['points'])
+    ref = make_solver('heat_param', backend='torch')
+    # copy the weights into the autograd solver
+    eng = fused._get_engine()
+    with torch.no_grad():
+        for (p_f, _), p_t in zip(eng.entries, [q for q in ref.model.conv_block.parameters()]):
+            pass
+    lin_f = fused.model.conv_block.linears
+    lin_t = ref.model.conv_block.linears
+    with torch.no_grad():
+        for a, b in zip(lin_f, lin_t):
+            b.weight.copy_(a.weight); b.bias.copy_(a.bias)
+    pts = torch.from_numpy(g['points']).cuda()
+    xs = [pts[:, i:i + 1].clone().requires_grad_() for i in range(pts.shape[1])]
+    u = ref.ctx.run(ref.model, ref.reshape_and_concat(xs))
+    r = ref.ctx.run(ref.equation, u, *xs)
+    l = torch.nn.functional.mse_loss(r, torch.zeros_like(r))
+    assert abs(float(l) - loss) <= 1e-5 * abs(loss)

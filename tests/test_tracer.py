@@ -1,0 +1,114 @@
+""" Tracer / lowering: symbolic D, partial derivatives, register programs (CPU only). """
+import numpy as np
+import pytest
+import torch
+
+import problems as P
+from pydens_b200 import tracer as T
+import emul_harness as E
+
+
+def eval_expr(e, env, memo=None):
+    memo = {} if memo is None else memo
+    if e in memo:
+        return memo[e]
+    k = e.kind
+    if k == 'const': r = np.full_like(env['x'][0], e.value)
+    elif k == 'coord': r = env['x'][e.value]
+    elif k == 'u': r = env['u'][e.value]
+    elif k == 'var': r = np.full_like(env['x'][0], env['v'][e.value])
+    elif k == 'powi': r = eval_expr(e.args[0], env, memo) ** e.value
+    else:
+        a = [eval_expr(x, env, memo) for x in e.args]
+        r = {'add': lambda: a[0] + a[1], 'sub': lambda: a[0] - a[1], 'mul': lambda: a[0] * a[1],
+             'div': lambda: a[0] / a[1], 'pow': lambda: a[0] ** a[1], 'neg': lambda: -a[0],
+             'sin': lambda: np.sin(a[0]), 'cos': lambda: np.cos(a[0]), 'tan': lambda: np.tan(a[0]),
+             'exp': lambda: np.exp(a[0]), 'log': lambda: np.log(a[0]), 'sqrt': lambda: np.sqrt(a[0]),
+             'tanh': lambda: np.tanh(a[0]), 'sigmoid': lambda: 1 / (1 + np.exp(-a[0])),
+             'abs': lambda: np.abs(a[0]), 'sign': lambda: np.sign(a[0])}[k]()
+    memo[e] = r
+    return r
+
+
+@pytest.mark.parametrize('name', list(P.PROBLEMS))
+def test_program_equals_expression_and_partials(name):
+    tr = E.traced_problem(name)
+    cfg = P.PROBLEMS[name]
+    total, n = cfg['ndims'] + cfg['nparams'], 50
+    rng = np.random.RandomState(0)
+    coords = np.stack([rng.uniform(lo, hi, n) for lo, hi in cfg['ranges']])
+    C = tr.channels
+    ujet = rng.normal(size=(C, n))
+    chan = {(): 0}
+    for d, col in enumerate(tr.dirs):
+        chan[(col,)] = 1 + d
+        if d < tr.ns:
+            chan[(col, col)] = 1 + tr.nf + d
+    vvals = {nm: 0.7 + i for i, nm in enumerate(tr.var_names)}
+
+    def env_of(uj):
+        return {'x': coords, 'u': {mi: uj[c] for mi, c in chan.items()}, 'v': vvals}
+    outs = T.run_program(tr.eq_prog, ujet, coords, [vvals[nm] for nm in tr.var_names])
+    r0 = eval_expr(tr.residual, env_of(ujet))
+    np.testing.assert_allclose(outs[0], r0, rtol=1e-12, atol=1e-12)
+    # partials w.r.t. every jet channel: central differences of the residual expression
+    for c in range(C):
+        h = 1e-6
+        up, um = ujet.copy(), ujet.copy()
+        up[c] += h; um[c] -= h
+        fd = (eval_expr(tr.residual, env_of(up)) - eval_expr(tr.residual, env_of(um))) / (2 * h)
+        np.testing.assert_allclose(outs[1 + c], fd, rtol=1e-5, atol=1e-6)
+    for i, nm in enumerate(tr.var_names):
+        h = 1e-6
+        vp, vm = dict(vvals), dict(vvals)
+        vp[nm] += h; vm[nm] -= h
+        e1 = env_of(ujet); e1['v'] = vp
+        e2 = env_of(ujet); e2['v'] = vm
+        fd = (eval_expr(tr.residual, e1) - eval_expr(tr.residual, e2)) / (2 * h)
+        np.testing.assert_allclose(outs[1 + C + i], fd, rtol=1e-5, atol=1e-6)
+    assert tr.n_slots <= T.MAX_SLOTS and len(tr.eq_prog) <= T.MAX_PROG
+
+
+def test_ic_program_is_the_jet_of_ic():
+    tr = E.traced_problem('heat2d')
+    n = 40
+    rng = np.random.RandomState(1)
+    coords = rng.uniform(0, 1, size=(3, n))
+    outs = T.run_program(tr.ic_prog, np.zeros((tr.channels, n)), coords, [])
+    x, y = coords[0], coords[1]
+    ic = 10 * x * y * (1 - x) * (1 - y)
+    np.testing.assert_allclose(outs[0], ic, rtol=1e-12)
+    # dirs = [x, y, t] with second order on x, y
+    assert tr.dirs == [0, 1, 2] and tr.ns == 2
+    np.testing.assert_allclose(outs[1], 10 * y * (1 - y) * (1 - 2 * x), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(outs[2], 10 * x * (1 - x) * (1 - 2 * y), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(outs[3], 0 * x, atol=1e-12)
+    np.testing.assert_allclose(outs[4], -20 * y * (1 - y), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(outs[5], -20 * x * (1 - x), rtol=1e-10, atol=1e-12)
+
+
+def test_not_lowerable_cases():
+    D = T.sym_D
+    with pytest.raises(T.NotLowerable):            # third order
+        T.trace(lambda f, x: D(D(D(f, x), x), x), 1, None)
+    with pytest.raises(T.NotLowerable):            # mixed second derivative
+        T.trace(lambda f, x, y: D(D(f, x), y), 2, None)
+    with pytest.raises(T.NotLowerable):            # data-dependent branch
+        T.trace(lambda f, x: f if x > 0 else -f, 1, None)
+    with pytest.raises(T.NotLowerable):            # unsupported torch function
+        T.trace(lambda f, x: torch.cumsum(f, 0), 1, None)
+    with pytest.raises(T.NotLowerable):            # variable inside the initial condition
+        T.trace(lambda f, x: D(f, x), 1, None, initial_condition=lambda: T.Sym(T.var('init')), ndims_spatial=0)
+
+
+def test_numpy_and_torch_entry_points_agree():
+    D = T.sym_D
+    a = T.trace(lambda f, x: D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x), 1, None)
+    b = T.trace(lambda f, x: D(f, x) - 2 * np.pi * np.cos(2 * np.pi * x), 1, None)
+    assert a.residual is b.residual                # hash-consed DAG: identical expression
+
+
+def test_derivative_with_respect_to_parameter_column_is_a_direction():
+    D = T.sym_D
+    tr = T.trace(lambda f, x, e: D(f, x) + D(f, e) * e, 2, None)
+    assert tr.dirs == [0, 1] and tr.ns == 0
