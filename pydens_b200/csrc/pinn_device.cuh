@@ -129,57 +129,77 @@ PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_
 }
 
 // ----------------------------------------------------------------------------------------------
-// Activations.  A hidden unit stores `s` (tanh/sigmoid: the activation value itself; sin: the
-// pre-activation) and everything else is rebuilt from it without another transcendental.
+// Activations, branch-free.  A hidden unit stores its activation VALUE a; the derivatives of the
+// activation are polynomials of a for tanh / sigmoid (constants for the identity), so ONE coefficient
+// set per layer replaces every switch in the inner loops:
+//     a   = ident ? z : p * tanh(q z) + r          (sigmoid(z) = 1/2 tanh(z/2) + 1/2)
+//     s1  = c0 + c1 a + c2 a^2 ;  s2 = s1 (d0 + d1 a) ;  s3 = s1 (e0 + e1 a + e2 a^2)
+// tanh   : s1 = 1 - a^2,  s2 = -2 a s1,         s3 = s1 (-2 + 6 a^2)
+// sigmoid: s1 = a - a^2,  s2 = s1 (1 - 2 a),    s3 = s1 (1 - 6 a + 6 a^2)
+// (s1, s2, s3 = first, second, third derivative of the activation w.r.t. its argument.)
 // ----------------------------------------------------------------------------------------------
-struct ActD { float a, s1, s2, s3; };   // value, sigma', sigma'', sigma'''
+struct ActD { float a, s1, s2, s3; };
+struct ActC { float p, q, r, c0, c1, c2, d0, d1, e0, e1, e2; bool ident; };
 
-PINN_HD float act_store(int act, float z) {
-    switch (act) {
-        case PINN_ACT_TANH:    return tanhf(z);
-        case PINN_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
-        default:               return z;           // NONE, SIN keep z
-    }
+PINN_HD ActC make_actc(int act) {
+    const bool th = act == PINN_ACT_TANH, sg = act == PINN_ACT_SIGMOID;
+    ActC k;
+    k.ident = !(th || sg);
+    k.p = sg ? 0.5f : 1.0f; k.q = sg ? 0.5f : 1.0f; k.r = sg ? 0.5f : 0.0f;
+    k.c0 = sg ? 0.0f : 1.0f; k.c1 = sg ? 1.0f : 0.0f; k.c2 = (th || sg) ? -1.0f : 0.0f;
+    k.d0 = sg ? 1.0f : 0.0f; k.d1 = (th || sg) ? -2.0f : 0.0f;
+    k.e0 = th ? -2.0f : (sg ? 1.0f : 0.0f); k.e1 = sg ? -6.0f : 0.0f; k.e2 = (th || sg) ? 6.0f : 0.0f;
+    return k;
 }
 
-PINN_HD ActD act_from_stored(int act, float s) {
-    ActD r;
-    switch (act) {
-        case PINN_ACT_TANH: {
-            r.a = s; r.s1 = fmaf(-s, s, 1.0f); r.s2 = -2.0f * s * r.s1;
-            r.s3 = -2.0f * r.s1 * fmaf(-3.0f * s, s, 1.0f);
-        } break;
-        case PINN_ACT_SIGMOID: {
-            r.a = s; r.s1 = s * (1.0f - s); r.s2 = r.s1 * fmaf(-2.0f, s, 1.0f);
-            r.s3 = r.s1 * fmaf(6.0f * s, s - 1.0f, 1.0f);
-        } break;
-        case PINN_ACT_SIN: {
-            float sn, cs;
+// tanh to ~1 ulp without branches: odd minimax polynomial below 0.55, 1 - 2/(e^{2|x|}+1) above.
+PINN_HD float tanh_acc(float x) {
+    const float ax = fabsf(x);
+    const float x2 = ax * ax;
+    float p = fmaf(x2, 1.6022265e-2f, -5.2653320e-2f);
+    p = fmaf(p, x2, 1.3314733e-1f);
+    p = fmaf(p, x2, -3.3332834e-1f);
+    const float small = fmaf(p * x2, ax, ax);
 #if defined(__CUDA_ARCH__)
-            sincosf(s, &sn, &cs);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));
+    const float big = fmaf(-2.0f, __frcp_rn(e + 1.0f), 1.0f);
 #else
-            sn = sinf(s); cs = cosf(s);
+    const float e = exp2f(ax * 2.8853900817779268f);
+    const float big = fmaf(-2.0f, 1.0f / (e + 1.0f), 1.0f);
 #endif
-            r.a = sn; r.s1 = cs; r.s2 = -sn; r.s3 = -cs;
-        } break;
-        default: { r.a = s; r.s1 = 1.0f; r.s2 = 0.0f; r.s3 = 0.0f; } break;
-    }
+    return copysignf(ax < 0.55f ? small : big, x);
+}
+
+PINN_HD float act_store(const ActC& k, float z) {
+    const float t = fmaf(k.p, tanh_acc(k.q * z), k.r);
+    return k.ident ? z : t;
+}
+
+PINN_HD ActD act_from_stored(const ActC& k, float a) {
+    ActD r;
+    r.a = a;
+    r.s1 = fmaf(fmaf(k.c2, a, k.c1), a, k.c0);
+    r.s2 = r.s1 * fmaf(k.d1, a, k.d0);
+    r.s3 = r.s1 * fmaf(fmaf(k.e2, a, k.e1), a, k.e0);
     return r;
 }
 
 // Load the stored (pre-activation) jet of one hidden unit and turn it into the post-activation
 // jet that feeds the next linear layer:  a, a_d = s1*z_d, a_dd = s2*z_d^2 + s1*z_dd.
 template <int NF, int NS>
-PINN_HD void load_post_jet(const float* __restrict__ row, int RS, int act, float (&a)[1 + NF + NS]) {
-    ActD f = act_from_stored(act, row[0]);
-    a[0] = f.a;
+PINN_HD void load_post_jet(const float* __restrict__ row, int RS, const ActC& k, float (&a)[1 + NF + NS]) {
+    const float av = row[0];
+    const float s1 = fmaf(fmaf(k.c2, av, k.c1), av, k.c0);
+    const float s2 = s1 * fmaf(k.d1, av, k.d0);
+    a[0] = av;
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
         float zd = row[(1 + d) * RS];
-        a[1 + d] = f.s1 * zd;
+        a[1 + d] = s1 * zd;
         if (d < NS) {
             float zdd = row[(1 + NF + d) * RS];
-            a[1 + NF + d] = fmaf(f.s2 * zd, zd, f.s1 * zdd);
+            a[1 + NF + d] = fmaf(s2 * zd, zd, s1 * zdd);
         }
     }
 }
@@ -191,7 +211,7 @@ PINN_HD void load_post_jet(const float* __restrict__ row, int RS, int act, float
 // ----------------------------------------------------------------------------------------------
 template <int NF, int NS, int NB>
 PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
-                              int n_in, const float* __restrict__ in_rows, int RS, int in_act,
+                              int n_in, const float* __restrict__ in_rows, int RS, const ActC& in_act,
                               float (&acc)[NB * 4][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
@@ -200,6 +220,7 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
 #pragma unroll
         for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
     }
+#pragma unroll 1
     for (int k = 0; k < n_in; ++k) {
         float a[C];
         load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
@@ -231,6 +252,7 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
 #pragma unroll
         for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
     }
+#pragma unroll 1
     for (int k = 0; k < n_in; ++k) {
         float x = coords[(size_t)k * RS];
         const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
@@ -257,28 +279,32 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
 
 // Store a block of freshly computed pre-activation jets: channel 0 goes through act_store().
 template <int NF, int NS, int NB>
-PINN_HD void store_block(float* __restrict__ out_rows, int RS, int act, int j0, int n_out,
+PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, int j0, int n_out,
                          const float (&acc)[NB * 4][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
     for (int j = 0; j < NB * 4; ++j) {
-        if (j0 + j < n_out) {
-            float* row = out_rows + (size_t)(j0 + j) * C * RS;
-            row[0] = act_store(act, acc[j][0]);
+        const float a = act_store(act, acc[j][0]);
+        const bool ok = j0 + j < n_out;
+        float* row = out_rows + (size_t)(ok ? j0 + j : j0) * C * RS;
+        if (ok) row[0] = a;
 #pragma unroll
-            for (int c = 1; c < C; ++c) row[(size_t)c * RS] = acc[j][c];
-        }
+        for (int c = 1; c < C; ++c)
+            if (ok) row[(size_t)c * RS] = acc[j][c];
     }
 }
 
 // One whole hidden (or input) linear layer, blocked over output units.
 template <int NF, int NS, int JF>
 PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
-                       bool in_is_coords, int in_act, const int* __restrict__ dir_col,
+                       bool in_is_coords, int in_act_id, const int* __restrict__ dir_col,
                        float* __restrict__ out_rows, int RS) {
     constexpr int NBMAX = JF / 4;
     const float* Wt = sw + L.wt_s;
     const float* bias = sw + L.b_s;
+    const ActC in_act = make_actc(in_act_id);
+    const ActC out_act = make_actc(L.act);
+#pragma unroll 1
     for (int j0 = 0; j0 < L.n_out; j0 += JF) {
         int nb = (L.n_out_p4 - j0) / 4;
         if (nb > NBMAX) nb = NBMAX;
@@ -291,7 +317,7 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
             else                                                                                    \
                 fwd_block_hidden<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,   \
                                              in_act, acc);                                          \
-            store_block<NF, NS, NB>(out_rows, RS, L.act, j0, L.n_out, acc);                         \
+            store_block<NF, NS, NB>(out_rows, RS, out_act, j0, L.n_out, acc);                         \
         }
         if (NBMAX >= 4 && nb == 4) PINN_FWD_CASE(4)
         else if (NBMAX >= 3 && nb == 3) PINN_FWD_CASE(3)
@@ -304,9 +330,10 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
 // Final linear layer (one output unit, no activation): the network jet N lands in registers.
 template <int NF, int NS>
 PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
-                       bool in_is_coords, int in_act, const int* __restrict__ dir_col, int RS,
+                       bool in_is_coords, int in_act_id, const int* __restrict__ dir_col, int RS,
                        float (&N)[1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
+    const ActC in_act = make_actc(in_act_id);
     const float* w = sw + L.w_s;            // reverse layout row 0 == the single weight row
     N[0] = sw[L.b_s];
 #pragma unroll
@@ -316,6 +343,7 @@ PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const fl
 #pragma unroll
         for (int d = 0; d < NF; ++d) N[1 + d] = w[dir_col[d]];
     } else {
+#pragma unroll 1
         for (int k = 0; k < L.n_in; ++k) {
             float a[C];
             load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
@@ -597,25 +625,33 @@ struct GradSink {
 };
 
 // Reverse of linear layer L (its output adjoints zb_L are already stored in out_rows):
-//   weight/bias gradients of L and — fused in the same loop — the adjoints of the layer below,
-//   which are pushed through that layer's activation and written over its stored jet in place.
-// JJ = output units handled per reduction batch (4 normally, 1 for the single-output top layer).
+//   weight AND bias gradients of L (the bias is column n_in of the same reduction batches: its
+//   "input jet" is (1, 0, …)) and — fused in the same loop — the adjoints of the layer below, pushed
+//   through that layer's activation and written over its stored jet in place.
+// JJ = output units per reduction batch (4 normally, 1 for the single-output top layer).
+// No guards in the inner loops: rows/columns past the end are read from clamped (valid) addresses,
+// meet zero-padded weights, and their reduction entries are dropped at the sink.
 template <int NF, int NS, int JJ>
-PINN_HD void bwd_layer(const DevLayer& L, int below_act, const float* __restrict__ sw,
+PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restrict__ sw,
                        const float* __restrict__ out_rows, float* __restrict__ in_rows, int RS,
                        const GradSink& sink) {
     constexpr int C = 1 + NF + NS;
     constexpr int JB = 8;
     const float* W = sw + L.w_s;
-    for (int m0 = 0; m0 < L.n_in; m0 += JB) {
+    const ActC below = make_actc(below_act_id);
+    const int n_cols = L.n_in + 1;                        // + bias column
+#pragma unroll 1
+    for (int m0 = 0; m0 < n_cols; m0 += JB) {
         float post[JB][C];
 #pragma unroll
         for (int mm = 0; mm < JB; ++mm) {
-            if (m0 + mm < L.n_in) {
-                load_post_jet<NF, NS>(in_rows + (size_t)(m0 + mm) * C * RS, RS, below_act, post[mm]);
-            } else {
+            const int m = m0 + mm;
+            const int mc = m < L.n_in ? m : L.n_in - 1;
+            load_post_jet<NF, NS>(in_rows + (size_t)mc * C * RS, RS, below, post[mm]);
+            if (m == L.n_in) {                            // bias column: jet (1, 0, …, 0)
+                post[mm][0] = 1.0f;
 #pragma unroll
-                for (int c = 0; c < C; ++c) post[mm][c] = 0.0f;
+                for (int c = 1; c < C; ++c) post[mm][c] = 0.0f;
             }
         }
         float acc[JB][C];
@@ -624,20 +660,17 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act, const float* __restrict
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[mm][c] = 0.0f;
 
+#pragma unroll 1
         for (int j0 = 0; j0 < L.n_out; j0 += JJ) {
             float v[JJ * JB];
 #pragma unroll
             for (int jj = 0; jj < JJ; ++jj) {
-                int j = j0 + jj;
+                const int j = j0 + jj;
+                const int jc = j < L.n_out ? j : L.n_out - 1;
+                const float* row = out_rows + (size_t)jc * C * RS;
                 float zb[C];
-                if (j < L.n_out) {
-                    const float* row = out_rows + (size_t)j * C * RS;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) zb[c] = row[(size_t)c * RS];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) zb[c] = 0.0f;
-                }
+                for (int c = 0; c < C; ++c) zb[c] = row[(size_t)c * RS];
                 const float4* wrow = reinterpret_cast<const float4*>(W + (size_t)j * L.n_in_p8 + m0);
                 float4 w0 = wrow[0], w1 = wrow[1];
                 float w[JB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -653,44 +686,49 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act, const float* __restrict
                 }
             }
             emit_entries<JJ * JB>(v, [&](int e, float t) {
-                int j = j0 + e / JB, m = m0 + e % JB;
-                if (j < L.n_out && m < L.n_in) sink.add(L.w_off + j * L.n_in + m, t);
+                const int j = j0 + e / JB, m = m0 + e % JB;
+                if (j < L.n_out && m <= L.n_in)
+                    sink.add(m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
             });
         }
         // adjoints of the layer below: through its activation, stored in place
 #pragma unroll
         for (int mm = 0; mm < JB; ++mm) {
-            if (m0 + mm < L.n_in) {
-                float* row = in_rows + (size_t)(m0 + mm) * C * RS;
-                float pre[C];
+            const bool ok = m0 + mm < L.n_in;
+            float* row = in_rows + (size_t)(ok ? m0 + mm : 0) * C * RS;
+            float pre[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
-                ActD f = act_from_stored(below_act, pre[0]);
-                float zb[C];
-                act_adjoint<NF, NS>(f, pre, acc[mm], zb);
+            for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
+            ActD f = act_from_stored(below, pre[0]);
+            float zb[C];
+            act_adjoint<NF, NS>(f, pre, acc[mm], zb);
 #pragma unroll
-                for (int c = 0; c < C; ++c) row[(size_t)c * RS] = zb[c];
-            }
+            for (int c = 0; c < C; ++c)
+                if (ok) row[(size_t)c * RS] = zb[c];
         }
     }
 }
 
-// Bias gradients of layer L: sum over points of the value-channel adjoint.
+// Bias gradients of a layer on their own (only the input layer with PINN_MAX_DIMS columns needs it).
 template <int NF, int NS>
 PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, int RS, const GradSink& sink) {
     constexpr int C = 1 + NF + NS;
+#pragma unroll 1
     for (int j0 = 0; j0 < L.n_out; j0 += 32) {
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            v[i] = (j0 + i < L.n_out) ? out_rows[(size_t)(j0 + i) * C * RS] : 0.0f;
+        for (int i = 0; i < 32; ++i) {
+            const int j = j0 + i < L.n_out ? j0 + i : L.n_out - 1;
+            v[i] = out_rows[(size_t)j * C * RS];
+        }
         emit_entries<32>(v, [&](int e, float t) {
             if (j0 + e < L.n_out) sink.add(L.b_off + j0 + e, t);
         });
     }
 }
 
-// Weight gradients of the FIRST linear layer: its input jet is (x, e_dir, 0).
+// Weight (and bias) gradients of the FIRST linear layer: its input jet is (x, e_dir, 0); the bias rides
+// in column n_in when n_in < PINN_MAX_DIMS.
 template <int NF, int NS>
 PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_rows,
                                const float* __restrict__ coords, int RS, const int* __restrict__ dir_col,
@@ -698,21 +736,18 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
     constexpr int C = 1 + NF + NS;
     float x[PINN_MAX_DIMS];
 #pragma unroll
-    for (int m = 0; m < PINN_MAX_DIMS; ++m) x[m] = (m < L.n_in) ? coords[(size_t)m * RS] : 0.0f;
+    for (int m = 0; m < PINN_MAX_DIMS; ++m)
+        x[m] = (m < L.n_in) ? coords[(size_t)m * RS] : (m == L.n_in ? 1.0f : 0.0f);
+#pragma unroll 1
     for (int j0 = 0; j0 < L.n_out; j0 += 4) {
         float v[4 * PINN_MAX_DIMS];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            int j = j0 + jj;
+            const int j = j0 + jj < L.n_out ? j0 + jj : L.n_out - 1;
+            const float* row = out_rows + (size_t)j * C * RS;
             float zb[1 + NF];
-            if (j < L.n_out) {
-                const float* row = out_rows + (size_t)j * C * RS;
 #pragma unroll
-                for (int c = 0; c < 1 + NF; ++c) zb[c] = row[(size_t)c * RS];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 1 + NF; ++c) zb[c] = 0.0f;
-            }
+            for (int c = 0; c < 1 + NF; ++c) zb[c] = row[(size_t)c * RS];
 #pragma unroll
             for (int m = 0; m < PINN_MAX_DIMS; ++m) {
                 float e = zb[0] * x[m];
@@ -722,10 +757,12 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
             }
         }
         emit_entries<4 * PINN_MAX_DIMS>(v, [&](int e, float t) {
-            int j = j0 + e / PINN_MAX_DIMS, m = e % PINN_MAX_DIMS;
-            if (j < L.n_out && m < L.n_in) sink.add(L.w_off + j * L.n_in + m, t);
+            const int j = j0 + e / PINN_MAX_DIMS, m = e % PINN_MAX_DIMS;
+            if (j < L.n_out && m <= L.n_in && m < PINN_MAX_DIMS)
+                sink.add(m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
         });
     }
+    if (L.n_in >= PINN_MAX_DIMS) bias_grad<NF, NS>(L, out_rows, RS, sink);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -747,6 +784,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
     float* scr = st + (size_t)P.row_scr * RS;
 
     // ---- forward through the hidden layers ----
+#pragma unroll 1
     for (int l = 0; l + 1 < Ln; ++l) {
         const DevLayer& L = P.layer[l];
         const float* in_rows = (l == 0) ? coords : units + (size_t)P.layer[l - 1].unit_base * C * RS;
@@ -798,19 +836,18 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
 #pragma unroll
         for (int c = 0; c < C; ++c) out_rows[(size_t)c * RS] = Nb[c];
     }
+#pragma unroll 1
     for (int l = Ln - 1; l >= 1; --l) {
         const DevLayer& L = P.layer[l];
         float* out_rows = units + (size_t)L.unit_base * C * RS;
         float* in_rows = units + (size_t)P.layer[l - 1].unit_base * C * RS;
         if (L.n_out == 1) bwd_layer<NF, NS, 1>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
         else              bwd_layer<NF, NS, 4>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
-        bias_grad<NF, NS>(L, out_rows, RS, sink);
     }
     {
         const DevLayer& L = P.layer[0];
         float* out_rows = units + (size_t)L.unit_base * C * RS;
         wgrad_input_layer<NF, NS>(L, out_rows, coords, RS, P.dir_col, sink);
-        bias_grad<NF, NS>(L, out_rows, RS, sink);
     }
     return r;
 }

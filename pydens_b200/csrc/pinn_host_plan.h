@@ -92,12 +92,12 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
         DevLayer& L = h.layer[l];
         L.n_in = s->widths[l]; L.n_out = s->widths[l + 1]; L.act = s->act[l];
         if (L.n_in < 1 || L.n_out < 1) PINN_PLAN_FAIL(PINN_E_INVALID, "layer %d width", l);
-        if (L.act < 0 || L.act > PINN_ACT_SIN) PINN_PLAN_FAIL(PINN_E_INVALID, "layer %d activation", l);
+        if (L.act < 0 || L.act > PINN_ACT_SIGMOID) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "layer %d: activation %d is not covered by the fused kernel", l, L.act);
         L.w_off = s->w_off[l]; L.b_off = s->b_off[l];
         if (L.w_off < 0 || L.w_off + L.n_in * L.n_out > s->n_params || L.b_off < 0 || L.b_off + L.n_out > s->n_params)
             PINN_PLAN_FAIL(PINN_E_INVALID, "layer %d offsets out of range", l);
         L.n_out_p4 = round_up_i(L.n_out, 4);
-        L.n_in_p8 = round_up_i(L.n_in, 8);
+        L.n_in_p8 = round_up_i(L.n_in + 1, 8);          // + the (zero) bias column of the reverse sweep
         L.wt_s = sw; sw += L.n_in * L.n_out_p4;
         L.w_s = sw;  sw += L.n_out_p4 * L.n_in_p8;
         L.b_s = sw;  sw += L.n_out_p4;

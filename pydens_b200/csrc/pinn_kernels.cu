@@ -27,13 +27,12 @@ namespace pinn {
 // Forward-only kernel (predict): u for explicit points.
 // ---------------------------------------------------------------------------------------------------
 template <bool GMEM>
-__global__ void __launch_bounds__(256, 1) forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(256, 1) forward_kernel(const __grid_constant__ DevPlan P, const FwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem);
-    const SmemLayout SL = smem_layout(a.plan->weights_floats, 0, 0,
-                                      GMEM ? a.plan->n_params : max(a.plan->n_params, a.rows_total * RS * nwarps));
-    stage_plan_and_weights(smem, SL, a.plan, a.params);
+    const SmemLayout SL = smem_layout(P.weights_floats, 0, 0,
+                                      GMEM ? P.n_params : max(P.n_params, a.rows_total * RS * nwarps));
+    stage_weights(smem, SL, P, a.params);
     const float* sw = smem + SL.weights_f;
     const long long gw = (long long)blockIdx.x * nwarps + warp;
     const long long total_warps = (long long)gridDim.x * nwarps;
@@ -51,10 +50,12 @@ __global__ void __launch_bounds__(256, 1) forward_kernel(const FwdArgs a) {
 }
 
 // Points the in-kernel sampler produces (for tests / replay).
-__global__ void sample_kernel(const DevPlan* plan, uint64_t seed, const uint64_t* step_ptr, uint64_t step_val,
-                              uint64_t point_offset, long long n_points, float* out) {
+struct SampleCols { PinnColumn c[PINN_MAX_DIMS]; int total; };
+
+__global__ void sample_kernel(const __grid_constant__ SampleCols cols, uint64_t seed, const uint64_t* step_ptr,
+                              uint64_t step_val, uint64_t point_offset, long long n_points, float* out) {
     const uint64_t step = step_ptr ? *step_ptr : step_val;
-    const int total = plan->total;
+    const int total = cols.total;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_points;
          p += (long long)gridDim.x * blockDim.x) {
         const uint64_t gidx = point_offset + (uint64_t)p;
@@ -66,7 +67,7 @@ __global__ void sample_kernel(const DevPlan* plan, uint64_t seed, const uint64_t
             b1 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3 | 1u, (uint32_t)seed,
                                (uint32_t)(seed >> 32));
         for (int k = 0; k < total; ++k)
-            out[(size_t)p * total + k] = sample_column(plan->cols[k], k, gidx, step, seed, b0, b1);
+            out[(size_t)p * total + k] = sample_column(cols.c[k], k, gidx, step, seed, b0, b1);
     }
 }
 
@@ -75,12 +76,6 @@ __global__ void record_loss_kernel(const float* out, int loss_idx, float* ring, 
     unsigned long long s = *step;
     ring[s % (unsigned long long)ring_len] = out[loss_idx];
     *step = s + 1ull;
-}
-
-__global__ void set_cols_kernel(DevPlan* plan, PinnColumn c0, PinnColumn c1, PinnColumn c2, PinnColumn c3,
-                                PinnColumn c4, PinnColumn c5, PinnColumn c6, PinnColumn c7) {
-    plan->cols[0] = c0; plan->cols[1] = c1; plan->cols[2] = c2; plan->cols[3] = c3;
-    plan->cols[4] = c4; plan->cols[5] = c5; plan->cols[6] = c6; plan->cols[7] = c7;
 }
 
 }  // namespace pinn
@@ -119,7 +114,6 @@ static const Variant* find_variant(int nf, int ns) {
 struct PinnPlan {
     PinnSpec spec;
     DevPlan h;
-    DevPlan* d;
     int device;
     const Variant* var;
     int sm_count;
@@ -130,8 +124,6 @@ struct PinnPlan {
     // forward kernel launch config
     bool fwd_gmem;
     int fwd_threads, fwd_smem_bytes, fwd_rows, fwd_row_scr;
-    PinnColumn cur_cols[PINN_MAX_DIMS];
-    bool cols_set;
 };
 
 
@@ -153,8 +145,6 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     p->spec = *s;
     p->device = device;
     p->var = var;
-    p->d = nullptr;
-    p->cols_set = false;
     DevPlan& h = p->h;
     cudaError_t e;
 
@@ -223,19 +213,12 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); }
     }
 
-    e = cudaMalloc(&p->d, sizeof(DevPlan));
-    if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaMalloc(plan): %s", cudaGetErrorString(e)); }
-    e = cudaMemcpy(p->d, &h, sizeof(DevPlan), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(p->d); delete p; return fail(PINN_E_CUDA, "cudaMemcpy(plan): %s", cudaGetErrorString(e)); }
-    for (int i = 0; i < PINN_MAX_DIMS; ++i) p->cur_cols[i] = h.cols[i];
-    p->cols_set = true;
     *out = p;
     return PINN_OK;
 }
 
 extern "C" int pinn_plan_destroy(PinnPlan* p) {
     if (!p) return PINN_OK;
-    if (p->d) cudaFree(p->d);
     delete p;
     return PINN_OK;
 }
@@ -270,24 +253,13 @@ extern "C" size_t pinn_workspace_bytes(const PinnPlan* p, int64_t n_points) {
 
 extern "C" int pinn_out_floats(const PinnPlan* p) { return p ? p->h.n_params + 4 : 0; }
 
-static bool cols_equal(const PinnColumn* a, const PinnColumn* b, int n) {
-    for (int i = 0; i < n; ++i)
-        if (a[i].kind != b[i].kind || a[i].a != b[i].a || a[i].b != b[i].b) return false;
-    return true;
-}
-
-static int apply_cols(PinnPlan* p, const PinnColumn* cols, cudaStream_t st) {
-    PinnColumn want[PINN_MAX_DIMS];
+// The sampler columns of a call are written into a by-value copy of the plan (kernel parameter).
+static int resolve_cols(const PinnPlan* p, const PinnColumn* cols, PinnColumn* out) {
     for (int i = 0; i < PINN_MAX_DIMS; ++i) {
-        if (cols && i < p->h.total) want[i] = cols[i];
-        else { want[i].kind = PINN_COL_UNIFORM; want[i].a = 0.0f; want[i].b = 1.0f; }
-        if (want[i].kind < 0 || want[i].kind > PINN_COL_CONST) return fail(PINN_E_INVALID, "column %d kind %d", i, want[i].kind);
+        if (cols && i < p->h.total) out[i] = cols[i];
+        else { out[i].kind = PINN_COL_UNIFORM; out[i].a = 0.0f; out[i].b = 1.0f; }
+        if (out[i].kind < 0 || out[i].kind > PINN_COL_CONST) return fail(PINN_E_INVALID, "column %d kind %d", i, out[i].kind);
     }
-    if (p->cols_set && cols_equal(want, p->cur_cols, PINN_MAX_DIMS)) return PINN_OK;
-    set_cols_kernel<<<1, 1, 0, st>>>(p->d, want[0], want[1], want[2], want[3], want[4], want[5], want[6], want[7]);
-    CUDA_TRY(cudaGetLastError());
-    for (int i = 0; i < PINN_MAX_DIMS; ++i) p->cur_cols[i] = want[i];
-    p->cols_set = true;
     return PINN_OK;
 }
 
@@ -300,14 +272,16 @@ extern "C" int pinn_step(const PinnPlan* cp, const float* params, const float* p
     PinnPlan* p = const_cast<PinnPlan*>(cp);
     if (!p || !params || !grads_and_loss || !workspace) return fail(PINN_E_INVALID, "null argument");
     if (n_points <= 0) return fail(PINN_E_INVALID, "n_points must be positive");
-    if (!aligned16(params) || !aligned16(grads_and_loss) || !aligned16(workspace) || (points && !aligned16(points)))
-        return fail(PINN_E_ALIGN, "device pointers must be 16-byte aligned");
+    if (!aligned16(params) || !aligned16(grads_and_loss) || !aligned16(workspace))
+        return fail(PINN_E_ALIGN, "params / grads_and_loss / workspace must be 16-byte aligned");
+    if (points && (((uintptr_t)points) & 3u)) return fail(PINN_E_ALIGN, "points must be 4-byte aligned");
     if (workspace_bytes < pinn_workspace_bytes(p, n_points))
         return fail(PINN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, pinn_workspace_bytes(p, n_points));
     cudaStream_t st = (cudaStream_t)stream;
-    if (!points) { int rc = apply_cols(p, cols, st); if (rc) return rc; }
+    DevPlan plan = p->h;
+    if (!points) { int rc = resolve_cols(p, cols, plan.cols); if (rc) return rc; }
     StepArgs a;
-    a.plan = p->d; a.params = params; a.points = points; a.seed = seed;
+    a.params = params; a.points = points; a.seed = seed;
     a.step_ptr = step_counter; a.step_val = step_value; a.point_offset = point_offset;
     a.n_points = n_points; a.inv_n = inv_global_n; a.out = grads_and_loss; a.residual = residual_out;
     a.ticket = reinterpret_cast<unsigned int*>(workspace);
@@ -316,7 +290,7 @@ extern "C" int pinn_step(const PinnPlan* cp, const float* params, const float* p
     a.n_wacc = p->n_wacc; a.rows_total = p->h.rows_total;
     const int grid = grid_for(p, n_points, p->threads);
     StepKernelFn fn = p->gmem ? p->var->gmem_fn : p->var->smem_fn;
-    fn<<<grid, p->threads, p->smem_bytes, st>>>(a);
+    fn<<<grid, p->threads, p->smem_bytes, st>>>(plan, a);
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;
 }
@@ -325,16 +299,17 @@ extern "C" int pinn_forward(const PinnPlan* p, const float* params, const float*
                             float* u_out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!p || !params || !points || !u_out || !workspace) return fail(PINN_E_INVALID, "null argument");
     if (n_points <= 0) return fail(PINN_E_INVALID, "n_points must be positive");
-    if (!aligned16(params) || !aligned16(points) || !aligned16(workspace)) return fail(PINN_E_ALIGN, "device pointers must be 16-byte aligned");
+    if (!aligned16(params) || !aligned16(workspace)) return fail(PINN_E_ALIGN, "params / workspace must be 16-byte aligned");
+    if (((uintptr_t)points) & 3u) return fail(PINN_E_ALIGN, "points must be 4-byte aligned");
     if (workspace_bytes < pinn_workspace_bytes(p, n_points)) return fail(PINN_E_WORKSPACE, "workspace too small");
     FwdArgs a;
-    a.plan = p->d; a.params = params; a.points = points; a.n_points = n_points; a.u_out = u_out;
+    a.params = params; a.points = points; a.n_points = n_points; a.u_out = u_out;
     a.spill = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_spill_off(p));
     a.rows_total = p->fwd_rows; a.row_scr = p->fwd_row_scr;
     const int grid = grid_for(p, n_points, p->fwd_threads);
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->fwd_gmem) forward_kernel<true><<<grid, p->fwd_threads, p->fwd_smem_bytes, st>>>(a);
-    else             forward_kernel<false><<<grid, p->fwd_threads, p->fwd_smem_bytes, st>>>(a);
+    if (p->fwd_gmem) forward_kernel<true><<<grid, p->fwd_threads, p->fwd_smem_bytes, st>>>(p->h, a);
+    else             forward_kernel<false><<<grid, p->fwd_threads, p->fwd_smem_bytes, st>>>(p->h, a);
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;
 }
@@ -346,11 +321,13 @@ extern "C" int pinn_sample(const PinnPlan* cp, const PinnColumn* cols, uint64_t 
     if (!p || !points_out) return fail(PINN_E_INVALID, "null argument");
     if (n_points <= 0) return fail(PINN_E_INVALID, "n_points must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = apply_cols(p, cols, st);
+    SampleCols sc;
+    sc.total = p->h.total;
+    int rc = resolve_cols(p, cols, sc.c);
     if (rc) return rc;
     long long blocks = (n_points + 255) / 256;
     if (blocks > 4 * p->sm_count) blocks = 4 * p->sm_count;
-    sample_kernel<<<(int)blocks, 256, 0, st>>>(p->d, seed, step_counter, step_value, point_offset, n_points, points_out);
+    sample_kernel<<<(int)blocks, 256, 0, st>>>(sc, seed, step_counter, step_value, point_offset, n_points, points_out);
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;
 }

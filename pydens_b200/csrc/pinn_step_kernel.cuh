@@ -12,7 +12,6 @@ namespace pinn {
 constexpr int RS = 32;                    // row stride of per-point storage: one warp tile
 
 struct StepArgs {
-    const DevPlan* plan;
     const float* params;
     const float* points;
     uint64_t seed;
@@ -31,7 +30,6 @@ struct StepArgs {
 };
 
 struct FwdArgs {
-    const DevPlan* plan;
     const float* params;
     const float* points;
     long long n_points;
@@ -82,14 +80,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Shared-memory carve-up (in floats) common to both kernels.
 struct SmemLayout {
-    int plan_f, weights_f, wacc_f, bar_f, storage_f, total_f;
+    int weights_f, wacc_f, bar_f, storage_f, total_f;
 };
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline SmemLayout smem_layout(int weights_floats, int n_out_floats, int n_wacc,
                                                   int storage_floats) {
     SmemLayout L;
-    L.plan_f = 0;
-    L.weights_f = align4((int)(sizeof(DevPlan) / 4));
+    L.weights_f = 0;
     L.wacc_f = L.weights_f + align4(weights_floats);
     L.bar_f = L.wacc_f + align4(n_out_floats * n_wacc);
     L.storage_f = L.bar_f + 4;
@@ -97,20 +94,16 @@ __host__ __device__ inline SmemLayout smem_layout(int weights_floats, int n_out_
     return L;
 }
 
-// Stage plan + parameters into shared memory.  Returns with __syncthreads() done.
-__device__ __forceinline__ void stage_plan_and_weights(float* smem, const SmemLayout& SL, const DevPlan* gplan,
-                                                       const float* params) {
+// Stage the parameters into shared memory: one TMA bulk copy of the flat buffer, then a re-layout
+// into the padded forward / reverse weight matrices.  Returns with __syncthreads() done.
+// The plan itself is a __grid_constant__ kernel parameter: every loop bound and program word is read
+// through the constant bank, i.e. provably warp-uniform.
+__device__ __forceinline__ void stage_weights(float* smem, const SmemLayout& SL, const DevPlan& P,
+                                              const float* params) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    // plan copy
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(gplan);
-        uint4* dst = reinterpret_cast<uint4*>(smem + SL.plan_f);
-        for (int i = tid; i < (int)(sizeof(DevPlan) / 16); i += nt) dst[i] = src[i];
-    }
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SL.bar_f);
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem + SL.plan_f);
     float* stage = smem + SL.storage_f;           // parameters land here first
     if (tid == 0) {
         uint32_t bytes = (uint32_t)P.n_params * 4u;
@@ -139,16 +132,14 @@ __device__ __forceinline__ void stage_plan_and_weights(float* smem, const SmemLa
 // The fit-step kernel.
 // ---------------------------------------------------------------------------------------------------
 template <int NF, int NS, bool GMEM, int MAXT, int JF>
-__global__ void __launch_bounds__(MAXT, 1) step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ DevPlan P, const StepArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-    const DevPlan& P = *reinterpret_cast<const DevPlan*>(smem);
-    // sizes needed for the carve-up come straight from the global plan (uniform loads)
-    const int n_out_floats = a.plan->n_params + 4;
-    const SmemLayout SL = smem_layout(a.plan->weights_floats, n_out_floats, a.n_wacc,
-                                      GMEM ? a.plan->n_params : max(a.plan->n_params, a.rows_total * RS * nwarps));
-    stage_plan_and_weights(smem, SL, a.plan, a.params);
+    const int n_out_floats = P.n_params + 4;
+    const SmemLayout SL = smem_layout(P.weights_floats, n_out_floats, a.n_wacc,
+                                      GMEM ? P.n_params : max(P.n_params, a.rows_total * RS * nwarps));
+    stage_weights(smem, SL, P, a.params);
     const float* sw = smem + SL.weights_f;
     float* wacc_all = smem + SL.wacc_f;
     for (int i = tid; i < n_out_floats * a.n_wacc; i += blockDim.x) wacc_all[i] = 0.0f;
@@ -242,7 +233,7 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const StepArgs a) {
 }
 
 
-typedef void (*StepKernelFn)(const StepArgs);
+typedef void (*StepKernelFn)(const DevPlan, const StepArgs);
 
 struct Variant {
     int nf, ns;

@@ -99,7 +99,7 @@ class TorchModel(ABC, nn.Module):
         return u
 
 
-_ACT_NAMES = {'tanh': 'tanh', 'sigmoid': 'sigmoid', 'sin': 'sin'}
+_ACT_NAMES = {'tanh': 'tanh', 'sigmoid': 'sigmoid'}          # activations the fused kernel covers
 
 
 class Sin(nn.Module):

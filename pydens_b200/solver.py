@@ -237,7 +237,7 @@ class Solver:
 
     def _constraint_loss(self, nums, xs, criterion):
         def _forward(*pts):
-            return self.model(self.reshape_and_concat(pts))
+            return self.model(self.reshape_and_concat(pts).to(self.device))
         total = 0
         zero = torch.zeros(1, device=self.device)
         for num in nums:
