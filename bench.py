@@ -110,7 +110,6 @@ def cpu_reference(workload, n_gpus, steps, warmup, budget_s=None):
     name, batch, lr = WORKLOADS[workload]
     cfg = P.PROBLEMS[name]
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(0)
     prob = ap.Problem(lambda u, *xs, D, V: cfg['equation'](u, *xs, D=D, V=V), ndims=cfg['ndims'],
                       nparams=cfg['nparams'], initial_condition=cfg['ic'], boundary_condition=cfg['bc'],
@@ -124,6 +123,18 @@ def cpu_reference(workload, n_gpus, steps, warmup, budget_s=None):
     def stream(i):
         cols = [torch.rand((sample_batch, 1)) * (hi - lo) + lo for lo, hi in ranges]
         return torch.cat(cols, dim=1)
+    # the reference leaves threading to PyTorch; on a many-core host the default (all cores) can be far
+    # from the best setting for these small ops, so give the baseline its best thread count
+    best, best_t = None, None
+    for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        torch.set_num_threads(nt)
+        ap.fit(prob, 1, sample_batch, lr=lr, point_stream=stream)
+        t = time.perf_counter()
+        ap.fit(prob, 2, sample_batch, lr=lr, point_stream=stream)
+        t = time.perf_counter() - t
+        if best_t is None or t < best_t:
+            best, best_t = nt, t
+    torch.set_num_threads(best)
     ap.fit(prob, warmup, sample_batch, lr=lr, point_stream=stream)
     t0 = time.perf_counter()
     done = 0
@@ -135,9 +146,10 @@ def cpu_reference(workload, n_gpus, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {'value': done * sample_batch / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d steps of batch %d (of the global %d) through oracle/autograd_port.py '
-                      '(reference loop on PyTorch-CPU autograd, %d threads)' % (done, sample_batch, gbatch, cores),
+    return {'value': done * sample_batch / dt, 'unit': 'points/s', 'cores': best, 'kind': 'port',
+            'sample': '%d steps of batch %d (of the global %d) through oracle/autograd_port.py (reference loop '
+                      'on PyTorch-CPU autograd; %d threads = best of a sweep on this %d-core host)'
+                      % (done, sample_batch, gbatch, best, cores),
             'ms_per_step': 1e3 * dt / done, 'steps': done}
 
 
@@ -157,6 +169,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     os.environ.setdefault('PYDENS_B200_PROGRESS', '0')
+    os.environ['NCCL_DEBUG'] = os.environ.get('PYDENS_B200_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
 
     if args.impl == 'reference':
         if rank != 0:
@@ -324,9 +337,10 @@ def main():
                'api': 'Solver.fit(niters=K, batch_size=B, sampler=<host batches in pinned memory>)'}
 
     clk = clocks.stop(t_load0, t_load1) if clocks else None
+    del graph, graph2                    # graphs hold captured NCCL work: drop them before tearing NCCL down
+    torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(dist, world)
         return
 
     peaks = {}
@@ -375,9 +389,20 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference(args.workload, 1, 40, 2, budget_s=20.0)
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _shutdown(dist, world)
+
+
+def _shutdown(dist, world):
+    """ Tear the process group down; never let a stuck NCCL teardown keep the job alive. """
+    if world <= 1:
+        return
+    t = threading.Thread(target=lambda: (dist.barrier(), dist.destroy_process_group()), daemon=True)
+    t.start()
+    t.join(20.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':

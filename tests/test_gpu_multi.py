@@ -1,0 +1,35 @@
+""" N>1 on real GPUs (skipped with fewer than 2 devices): the sharded fit (NCCL all-reduce of the
+[grads | loss] buffer, captured in the CUDA graph) follows the single-GPU fit on the same global batch. """
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(world, out):
+    env = dict(os.environ, PYDENS_B200_PROGRESS='0')
+    script = os.path.join(ROOT, 'tools', 'check_dp.py')
+    if world == 1:
+        cmd = [sys.executable, script, out]
+    else:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+               '--master-addr', '127.0.0.1', '--master-port', str(29600 + os.getpid() % 300), script, out]
+    subprocess.check_call(cmd, env=env, timeout=600)
+    return json.load(open(out))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_fit_matches_single_gpu(tmp_path):
+    one = _run(1, str(tmp_path / 'w1.json'))
+    two = _run(2, str(tmp_path / 'w2.json'))
+    a, b = np.asarray(one['losses']), np.asarray(two['losses'])
+    assert a.shape == b.shape == (30,)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-4
+    assert abs(one['params_norm'] - two['params_norm']) <= 1e-4 * one['params_norm']
