@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   3
+#define PINN_ABI_VERSION   4
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -129,8 +129,9 @@ typedef struct PinnColumn {
  * Programs: scratch slots 0..C-1 (C = 1 + nf + ns) are preloaded with the jet of u before
  *   eq_prog runs.  eq_out[0] is the slot of the residual r, eq_out[1+c] the slot of
  *   dr/d(jet channel c), eq_out[1+C+i] the slot of dr/dV_i.  ic_prog runs before u is
- *   assembled (it reads only PINN_OP_COORD leaves); ic_out[c] is the slot holding channel c
- *   of the jet of ic.
+ *   assembled; ic_out[c] is the slot holding channel c of the jet of ic.  When the initial condition
+ *   uses variables (ic_has_vars; e.g. README.md:112-118 `V('init', ...)`), ic_out[C*(1+i) + c] is the
+ *   slot of d(ic jet channel c)/dV_i and those slots lie above every slot eq_prog writes.
  */
 typedef struct PinnSpec {
     int32_t  abi_version;
@@ -157,7 +158,8 @@ typedef struct PinnSpec {
     int32_t   eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
     int32_t   n_ic;
     PinnInstr ic_prog[PINN_MAX_PROG];
-    int32_t   ic_out[1 + 2 * PINN_MAX_DIRS];
+    int32_t   ic_out[(1 + 2 * PINN_MAX_DIRS) * (1 + PINN_MAX_VARS)];
+    int32_t   ic_has_vars;
     int32_t   n_slots;          /* scratch slots either program may touch */
 } PinnSpec;
 

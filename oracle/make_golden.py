@@ -74,7 +74,7 @@ def build(name, seed=0):
     cfg = P.PROBLEMS[name]
     torch.manual_seed(seed)
     solver = ref.Solver(P.bind(name, ref.D, ref_V), ndims=cfg['ndims'], nparams=cfg['nparams'],
-                        initial_condition=cfg['ic'], boundary_condition=cfg['bc'], domain=cfg['domain'],
+                        initial_condition=P.make_ic(name, ref_V), boundary_condition=cfg['bc'], domain=cfg['domain'],
                         layout=cfg['layout'], features=cfg['features'], activation=cfg['activation'])
     if 'log_scale' in cfg:
         with torch.no_grad():

@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3}
@@ -46,7 +46,8 @@ class PinnSpec(C.Structure):
         ('eq_out', C.c_int32 * (1 + 1 + 2 * MAX_DIRS + MAX_VARS)),
         ('n_ic', C.c_int32),
         ('ic_prog', PinnInstr * MAX_PROG),
-        ('ic_out', C.c_int32 * (1 + 2 * MAX_DIRS)),
+        ('ic_out', C.c_int32 * ((1 + 2 * MAX_DIRS) * (1 + MAX_VARS))),
+        ('ic_has_vars', C.c_int32),
         ('n_slots', C.c_int32),
     ]
 
@@ -186,6 +187,7 @@ def build_spec(widths, acts, ndims, nparams, has_bc, bc_value, has_ic, domain, t
         s.n_ic = len(traced.ic_prog)
         for i, slot in enumerate(traced.ic_prog.outs):
             s.ic_out[i] = slot
+        s.ic_has_vars = int(traced.ic_has_vars)
     s.n_slots = max(traced.n_slots, traced.channels)
     return s
 

@@ -61,7 +61,8 @@ struct alignas(16) DevPlan {
     int var_off[PINN_MAX_VARS];
     float lo[PINN_MAX_DIMS], hi[PINN_MAX_DIMS], inv_w2[PINN_MAX_DIMS];
     int eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
-    int ic_out[1 + 2 * PINN_MAX_DIRS];
+    int ic_out[(1 + 2 * PINN_MAX_DIRS) * (1 + PINN_MAX_VARS)];
+    int ic_has_vars;
     PinnColumn cols[PINN_MAX_DIMS];     // sampler columns of the current call
     DevLayer layer[PINN_MAX_LAYERS];
     PinnInstr eq[PINN_MAX_PROG];
@@ -825,6 +826,16 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
 #pragma unroll
     for (int i = 0; i < PINN_MAX_VARS; ++i)
         if (i < P.n_vars) part.vbar[i] = fmaf(rb, scr[(size_t)P.eq_out[1 + C + i] * RS], part.vbar[i]);
+    if (P.ic_has_vars) {                       // u_c = S v_c + ic_c: variables of the initial condition
+#pragma unroll
+        for (int i = 0; i < PINN_MAX_VARS; ++i) {
+            if (i < P.n_vars) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    part.vbar[i] = fmaf(ub[c], scr[(size_t)P.ic_out[C * (1 + i) + c] * RS], part.vbar[i]);
+            }
+        }
+    }
 
     float Nb[C];
     part.sbar += ansatz_adjoint<NF, NS>(P, as, ub, Nb);

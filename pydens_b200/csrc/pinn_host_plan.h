@@ -56,11 +56,11 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     if (s->n_slots < C || s->n_slots > PINN_MAX_SLOTS) PINN_PLAN_FAIL(PINN_E_INVALID, "n_slots %d", s->n_slots);
     int rc;
     if ((rc = validate_prog(s->eq_prog, s->n_eq, s->n_slots, total, s->n_vars, "eq_prog", msg, msg_len))) return rc;
-    if (s->has_ic && (rc = validate_prog(s->ic_prog, s->n_ic, s->n_slots, total, 0, "ic_prog", msg, msg_len))) return rc;
+    if (s->has_ic && (rc = validate_prog(s->ic_prog, s->n_ic, s->n_slots, total, s->n_vars, "ic_prog", msg, msg_len))) return rc;
     for (int i = 0; i < 1 + C + s->n_vars; ++i)
         if (s->eq_out[i] < 0 || s->eq_out[i] >= s->n_slots) PINN_PLAN_FAIL(PINN_E_INVALID, "eq_out[%d]", i);
     if (s->has_ic)
-        for (int c = 0; c < C; ++c)
+        for (int c = 0; c < C * (1 + (s->ic_has_vars ? s->n_vars : 0)); ++c)
             if (s->ic_out[c] < 0 || s->ic_out[c] >= s->n_slots) PINN_PLAN_FAIL(PINN_E_INVALID, "ic_out[%d]", c);
     if (s->log_scale_off < 0 || s->log_scale_off >= s->n_params) PINN_PLAN_FAIL(PINN_E_INVALID, "log_scale_off");
     for (int i = 0; i < s->n_vars; ++i)
@@ -73,6 +73,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     h.nf = s->nf; h.ns = s->ns; h.n_params = s->n_params; h.log_scale_off = s->log_scale_off;
     h.n_vars = s->n_vars; h.n_eq = s->n_eq; h.n_ic = s->has_ic ? s->n_ic : 0; h.n_slots = s->n_slots;
     h.bc = s->bc_value;
+    h.ic_has_vars = (s->has_ic && s->ic_has_vars) ? 1 : 0;
     h.t0 = s->dom_lo[s->ndims - 1];
     for (int d = 0; d < PINN_MAX_DIRS; ++d) h.dir_col[d] = d < s->nf ? s->dir_col[d] : 0;
     for (int i = 0; i < PINN_MAX_VARS; ++i) h.var_off[i] = i < s->n_vars ? s->var_off[i] : 0;

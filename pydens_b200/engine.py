@@ -220,19 +220,24 @@ class FusedEngine:
         if use_graph:
             one_step(0)                               # real step 0: also materialises optimizer state
             done = 1
+            # several steps per graph when there are many: one replay = G optimizer steps, which matters in
+            # the launch-bound small-batch regime (README example: batch 100 x 1500 iterations)
+            per_graph = int(os.environ.get('PYDENS_B200_GRAPH_STEPS', '0')) or (4 if niters - 1 >= 64 else 1)
             graph = None
             try:
                 torch.cuda.synchronize(self.device)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    one_step(1)
+                    for k in range(per_graph):
+                        one_step(1 + k)
             except Exception:                         # capture unsupported here: plain launches
                 graph = None
                 torch.cuda.synchronize(self.device)
             if graph is not None:
-                for _ in range(niters - 1):
+                for _ in range((niters - 1) // per_graph):
                     graph.replay()
-                done = niters
+                done = 1 + ((niters - 1) // per_graph) * per_graph
+                del graph
         if done < niters:
             from .solver import _progress
             for i in _progress(niters - done):

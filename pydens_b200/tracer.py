@@ -585,7 +585,8 @@ class TracedEquation:
         self.ns = 0                 # how many of them also carry a second derivative
         self.var_names = []         # variables used by the equation, in VAR-operand order
         self.eq_prog = None         # outputs: [r, dr/dchannel_0 .. dr/dchannel_{C-1}, dr/dV_0 ..]
-        self.ic_prog = None         # outputs: jet of ic (C entries) or None
+        self.ic_prog = None         # outputs: jet of ic (C entries) [+ C partials per variable] or None
+        self.ic_has_vars = False
         self.n_slots = 0
 
     @property
@@ -635,29 +636,36 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
             chan[uleaf((col, col))] = 1 + nf + d
     by_channel = {v: k for k, v in chan.items()}
 
-    T.var_names = sorted({l.value for l in leaves(res, ('var',))})
-    if len(T.var_names) > 4:
-        raise NotLowerable('more than 4 trainable variables in the equation')
-    var_index = {n: i for i, n in enumerate(T.var_names)}
-
-    outputs = [res] + [diff_leaf(res, by_channel[c]) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
-    T.eq_prog = lower(outputs, chan, var_index, C)
-    T.n_slots = T.eq_prog.n_slots
-
+    # the initial condition is traced first: its variables join the equation's (README.md:112-118)
+    ic = None
     if initial_condition is not None:
         if callable(initial_condition):
             ic_out = run(initial_condition, *xs[:ndims_spatial])
             ic = ic_out.expr if isinstance(ic_out, Sym) else _as_expr(ic_out)
         else:
             ic = const(float(np.float32(initial_condition)))
-        if leaves(ic, ('var',)):
-            raise NotLowerable('V variables inside initial_condition are not supported by the fused path yet')
         if leaves(ic, ('u',)):
             raise NotLowerable('initial_condition must not depend on the solution')
+    ic_vars = {l.value for l in leaves(ic, ('var',))} if ic is not None else set()
+    T.var_names = sorted({l.value for l in leaves(res, ('var',))} | ic_vars)
+    if len(T.var_names) > 4:
+        raise NotLowerable('more than 4 trainable variables')
+    var_index = {n: i for i, n in enumerate(T.var_names)}
+
+    outputs = [res] + [diff_leaf(res, by_channel[c]) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
+    T.eq_prog = lower(outputs, chan, var_index, C)
+    T.n_slots = T.eq_prog.n_slots
+
+    if ic is not None:
         jet = [ic]
         firsts = [diff_coord(ic, col) for col in T.dirs]
         jet += firsts
         jet += [diff_coord(firsts[d], T.dirs[d]) for d in range(ns)]
-        T.ic_prog = lower(jet, {}, {}, C)
+        T.ic_has_vars = bool(ic_vars)
+        base = C
+        if T.ic_has_vars:               # partials w.r.t. every variable; slots above the equation's
+            jet = jet + [diff_leaf(j, var(n)) for n in T.var_names for j in jet]
+            base = T.eq_prog.n_slots
+        T.ic_prog = lower(jet, {}, var_index, base)
         T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
     return T

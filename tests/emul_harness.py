@@ -33,9 +33,10 @@ def lib():
 def traced_problem(name):
     cfg = P.PROBLEMS[name]
     total = cfg['ndims'] + cfg['nparams']
-    nsp = cfg['ndims'] - 1 if cfg['ic'] is not None else cfg['ndims']
-    eq = P.bind(name, T.sym_D, lambda n, init: T.Sym(T.var(n)))
-    return T.trace(eq, total, None, initial_condition=cfg['ic'], ndims_spatial=nsp)
+    nsp = cfg['ndims'] - 1 if P.has_ic(name) else cfg['ndims']
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    eq = P.bind(name, T.sym_D, sym_V)
+    return T.trace(eq, total, None, initial_condition=P.make_ic(name, sym_V), ndims_spatial=nsp)
 
 
 def spec_for(name):
@@ -48,7 +49,7 @@ def spec_for(name):
     if isinstance(dom[0], (int, float)):
         dom = [tuple(dom)] * cfg['ndims']
     return N.build_spec(widths, acts, cfg['ndims'], cfg['nparams'], cfg['bc'] is not None,
-                        cfg['bc'] if cfg['bc'] is not None else 0.0, cfg['ic'] is not None, dom, tr)
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, P.has_ic(name), dom, tr)
 
 
 def emul_step(spec, params, points):

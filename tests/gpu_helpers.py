@@ -14,7 +14,7 @@ def make_solver(name, params=None, backend='fused', seed=0, **kw):
     cfg = P.PROBLEMS[name]
     torch.manual_seed(seed)
     solver = Solver(P.bind(name, D, pkg_V), ndims=cfg['ndims'], nparams=cfg['nparams'],
-                    initial_condition=cfg['ic'], boundary_condition=cfg['bc'], domain=cfg['domain'],
+                    initial_condition=P.make_ic(name, pkg_V), boundary_condition=cfg['bc'], domain=cfg['domain'],
                     layout=cfg['layout'], features=cfg['features'], activation=cfg['activation'],
                     device='cuda', backend=backend, seed=1234, **kw)
     if params is not None:

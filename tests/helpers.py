@@ -16,10 +16,13 @@ def load_golden(name):
 
 def oracle_problem(name, dtype=torch.float32, params=None):
     cfg = P.PROBLEMS[name]
+    holder = {}
+    ic = P.make_ic(name, lambda n, init: holder['prob'].V(n, init))
     prob = ap.Problem(lambda u, *xs, D, V: cfg['equation'](u, *xs, D=D, V=V),
-                      ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=cfg['ic'],
+                      ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=ic,
                       boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
                       activation=cfg['activation'], dtype=dtype, variables=cfg.get('variables'))
+    holder['prob'] = prob
     if params is not None:
         prob.load_flat(torch.as_tensor(params))
     return prob

@@ -52,6 +52,14 @@ def _nonlinear(f, x, y, D, V):
             + torch.tanh(D(D(f, y), y)) * 0.5 - (2.0 - y) ** 3 + torch.cos(f) / 3.0 + abs(fx) * 0.1)
 
 
+def _heat1d_icvar(f, x, t, D, V):                    # variables in the equation AND in the initial condition
+    return 0.3 * D(D(f, x), x) - D(f, t) + V('src', 0.1) * torch.sin(x)
+
+
+def _icf_heat1d(V):                                  # README.md:112-118 style: V inside initial_condition
+    return lambda x: V('amp', 0.7) * torch.sin(PI * x) + V('shift', 0.2) ** 2
+
+
 def _ic_heat(x, y):
     return 10 * x * y * (1 - x) * (1 - y)
 
@@ -89,16 +97,19 @@ PROBLEMS = {
     'burgers': dict(equation=_burgers, ndims=2, nparams=0, ic=_ic_burgers, bc=0.5,
                     domain=[(-1, 2), (0, 3)], features=[8, 9, 1], activation='Tanh', layout='fafaf',
                     ranges=[(-1, 2), (0, 3)], log_scale=0.3),
+    'heat1d_icvar': dict(equation=_heat1d_icvar, ndims=2, nparams=0, ic=None, ic_factory=_icf_heat1d, bc=0.0,
+                         domain=(0, 1), features=[9, 7, 1], activation='Tanh', layout='fafaf',
+                         variables={'amp': 0.7, 'shift': 0.2, 'src': 0.1}, ranges=[(0, 1), (0, 1)], log_scale=-0.2),
     'nonlinear': dict(equation=_nonlinear, ndims=2, nparams=0, ic=None, bc=None, domain=(0, 1),
                       features=[7, 5, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1), (0, 1)]),
 }
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
-                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64}
+                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
-               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05)}
+               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02)}
 
 
 def make_points(name, batch, seed):
@@ -107,6 +118,20 @@ def make_points(name, batch, seed):
     rng = np.random.RandomState(seed)
     cols = [rng.uniform(lo, hi, size=(batch, 1)) for lo, hi in cfg['ranges']]
     return np.concatenate(cols, axis=1).astype(np.float32)
+
+
+def make_ic(name, V):
+    """ initial_condition argument of the problem (callable / number / None); problems whose initial
+    condition uses trainable variables build it from the V token of the implementation under test. """
+    cfg = PROBLEMS[name]
+    if 'ic_factory' in cfg:
+        return cfg['ic_factory'](V)
+    return cfg['ic']
+
+
+def has_ic(name):
+    cfg = PROBLEMS[name]
+    return cfg['ic'] is not None or 'ic_factory' in cfg
 
 
 def bind(name, D, V):

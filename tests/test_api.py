@@ -81,8 +81,8 @@ def test_lowering_decisions():
     assert s._traced is None and 'mixed' in s._lower_error
     s = Solver(lambda f, t: D(f, t), ndims=1, initial_condition=lambda: V('init', data=torch.Tensor([3.0])),
                device='cpu')
-    assert s._traced is None                                      # V inside the initial condition
-    s.fit(niters=2, batch_size=8)                                 # … still trains on the autograd path
+    assert s._traced is not None and s._traced.var_names == ['init'] and s._traced.ic_has_vars
+    s.fit(niters=2, batch_size=8)                                 # (CPU here: autograd path)
     s = Solver(pde, ndims=2, layout='faR fa+ f', features=[6, 6, 1], device='cpu')
     assert s._traced is None and 'dense chain' in s._lower_error
     s.fit(niters=2, batch_size=8)

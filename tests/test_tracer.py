@@ -97,8 +97,32 @@ def test_not_lowerable_cases():
         T.trace(lambda f, x: f if x > 0 else -f, 1, None)
     with pytest.raises(T.NotLowerable):            # unsupported torch function
         T.trace(lambda f, x: torch.cumsum(f, 0), 1, None)
-    with pytest.raises(T.NotLowerable):            # variable inside the initial condition
-        T.trace(lambda f, x: D(f, x), 1, None, initial_condition=lambda: T.Sym(T.var('init')), ndims_spatial=0)
+    with pytest.raises(T.NotLowerable):            # initial condition depending on the solution
+        T.trace(lambda f, x: D(f, x), 1, None, initial_condition=lambda: T.Sym(T.uleaf()), ndims_spatial=0)
+
+
+def test_variables_inside_initial_condition():
+    D = T.sym_D
+    tr = T.trace(lambda f, x, t: D(D(f, x), x) - D(f, t) + T.Sym(T.var('src')), 2, None,
+                 initial_condition=lambda x: T.Sym(T.var('amp')) * np.sin(x) + T.Sym(T.var('shift')) ** 2,
+                 ndims_spatial=1)
+    assert tr.var_names == ['amp', 'shift', 'src'] and tr.ic_has_vars
+    C = tr.channels
+    assert len(tr.ic_prog.outs) == C * (1 + 3)
+    assert min(tr.ic_prog.outs) >= tr.eq_prog.n_slots          # never clobbered by the residual program
+    n = 16
+    coords = np.random.RandomState(0).uniform(0, 1, size=(2, n))
+    vals = [0.7, 0.2, 0.1]
+    outs = T.run_program(tr.ic_prog, np.zeros((C, n)), coords, vals)
+    x = coords[0]
+    np.testing.assert_allclose(outs[0], 0.7 * np.sin(x) + 0.04, rtol=1e-12)
+    # dirs: x carries first+second order, t first order -> channels [v, x, t, xx]
+    assert tr.dirs == [0, 1] and tr.ns == 1
+    np.testing.assert_allclose(outs[1], 0.7 * np.cos(x), rtol=1e-12)
+    np.testing.assert_allclose(outs[3], -0.7 * np.sin(x), rtol=1e-12)
+    np.testing.assert_allclose(outs[C + 0], np.sin(x), rtol=1e-12)        # d ic / d amp
+    np.testing.assert_allclose(outs[2 * C + 0], 0.4 * np.ones(n), rtol=1e-12)  # d ic / d shift
+    np.testing.assert_allclose(outs[3 * C + 0], 0 * x, atol=1e-15)       # d ic / d src
 
 
 def test_numpy_and_torch_entry_points_agree():
