@@ -161,6 +161,8 @@ def main():
     ap_.add_argument('--warmup', type=int, default=5)
     ap_.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap_.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
+    ap_.add_argument('--global-batch', type=int, default=0,
+                     help='fix the GLOBAL batch (strong scaling); default: per-GPU batch of the workload (weak)')
     ap_.add_argument('--no-cpu-baseline', action='store_true')
     ap_.add_argument('--no-e2e', action='store_true')
     args = ap_.parse_args()
@@ -200,7 +202,7 @@ def main():
     from pydens_b200 import Solver, D, V, _native
     name, batch, lr = WORKLOADS[args.workload]
     cfg = P.PROBLEMS[name]
-    gbatch = batch * world
+    gbatch = args.global_batch if args.global_batch else batch * world
     torch.manual_seed(0)
     solver = Solver(P.bind(name, D, lambda n, init: V(n, data=torch.Tensor([init]))), ndims=cfg['ndims'],
                     nparams=cfg['nparams'], initial_condition=cfg['ic'], boundary_condition=cfg['bc'],
@@ -364,9 +366,10 @@ def main():
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms_total / K, 'higher_is_better': True,
+        'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': dict(describe(args.workload, world),
+        'config': dict(describe(args.workload, world), global_batch=gbatch,
                        inputs='HBM-resident pool of %d distinct batches (%.0f MB%s), one per step; '
                               'in-kernel Philox sampling variant reported as value_sampled'
                               % (pool_n, pool.numel() * 4 / 1e6, ' > L2' if pool.numel() * 4 > 126e6 else ''),

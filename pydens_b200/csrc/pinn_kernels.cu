@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 #include "pinn_step_kernel.cuh"
@@ -178,7 +179,12 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
             if (SL.total_f * 4 <= budget) { best_nw = nw; best_nwacc = nwacc; }
         }
     }
-    if (best_nw >= 4 || (best_nw >= 2 && max_warps <= 4)) {
+    // PINN_FORCE_MODE=smem|gmem overrides the placement heuristic (experiments only)
+    const char* force = getenv("PINN_FORCE_MODE");
+    bool use_smem = best_nw >= 4 || (best_nw >= 2 && max_warps <= 4);
+    if (force && !strcmp(force, "smem") && best_nw >= 1) use_smem = true;
+    if (force && !strcmp(force, "gmem")) use_smem = false;
+    if (use_smem) {
         p->gmem = false; p->threads = best_nw * 32; p->n_wacc = best_nwacc;
         SmemLayout SL = smem_layout(h.weights_floats, n_out_floats, best_nwacc,
                                     h.rows_total * RS * best_nw > h.n_params ? h.rows_total * RS * best_nw : h.n_params);

@@ -17,6 +17,7 @@ import torch
 from . import _native
 
 _GRAPH_MIN_ITERS = 8
+_HOST_GRAPH_MIN_ITERS = 2000        # host-sampler mode: 4 captures (~20 ms each) only pay off on long fits
 
 
 def _dist():
@@ -240,6 +241,7 @@ class FusedEngine:
                 del graph
         if done < niters:
             from .solver import _progress
+            stage_graphs = None
             for i in _progress(niters - done):
                 if host_sampler is not None:
                     k = i % len(pinned)
@@ -251,11 +253,31 @@ class FusedEngine:
                         pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)))
                         src = pinned[k]
                     dev_pts[k].copy_(src[point_offset:point_offset + local_n], non_blocking=True)
-                    one_step(done + i, dev_pts[k])
+                    if stage_graphs is not None:
+                        stage_graphs[k].replay()
+                    else:
+                        one_step(done + i, dev_pts[k])
                     zero_host[done + i:done + i + 1].copy_(self.out[loss_idx:loss_idx + 1], non_blocking=True)
                     events[k].record()
+                    # after the first (eager) step the optimizer state exists: capture the compute part of the
+                    # step once per staging buffer, so that every later step is copy -> replay -> loss read
+                    if (i == 0 and stage_graphs is None and capturable and not nums and niters - done >= _HOST_GRAPH_MIN_ITERS
+                            and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'):
+                        try:
+                            torch.cuda.synchronize(self.device)
+                            graphs = []
+                            for kk in range(len(pinned)):
+                                g = torch.cuda.CUDAGraph()
+                                with torch.cuda.graph(g):
+                                    one_step(0, dev_pts[kk])
+                                graphs.append(g)
+                            stage_graphs = graphs
+                        except Exception:               # capture unsupported here: keep plain launches
+                            stage_graphs = None
+                            torch.cuda.synchronize(self.device)
                 else:
                     one_step(done + i)
+            stage_graphs = None
         self.steps_done = start + niters
         torch.cuda.synchronize(self.device)
         if host_sampler is not None:
