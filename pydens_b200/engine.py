@@ -195,7 +195,9 @@ class FusedEngine:
         if host_sampler is not None:
             n_stage = 4
             pinned = [torch.empty((batch_size, total), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
-            events = [torch.cuda.Event() for _ in range(n_stage)]
+            events = [torch.cuda.Event() for _ in range(n_stage)]          # H2D of buffer k has completed
+            free_ev = [torch.cuda.Event() for _ in range(n_stage)]         # compute no longer reads dev_pts[k]
+            copy_stream = torch.cuda.Stream(device=self.device)
             dev_pts = [torch.empty((local_n, total), dtype=torch.float32, device=self.device) for _ in range(n_stage)]
             zero_host = torch.zeros(max(niters, 1), dtype=torch.float32).pin_memory()
 
@@ -252,13 +254,19 @@ class FusedEngine:
                     else:
                         pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)))
                         src = pinned[k]
-                    dev_pts[k].copy_(src[point_offset:point_offset + local_n], non_blocking=True)
+                    # the batch travels on its own stream so that the copy of step i+1 overlaps step i
+                    cur = torch.cuda.current_stream(self.device)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(free_ev[k])
+                        dev_pts[k].copy_(src[point_offset:point_offset + local_n], non_blocking=True)
+                        events[k].record(copy_stream)
+                    cur.wait_event(events[k])
                     if stage_graphs is not None:
                         stage_graphs[k].replay()
                     else:
                         one_step(done + i, dev_pts[k])
+                    free_ev[k].record(cur)
                     zero_host[done + i:done + i + 1].copy_(self.out[loss_idx:loss_idx + 1], non_blocking=True)
-                    events[k].record()
                     # after the first (eager) step the optimizer state exists: capture the compute part of the
                     # step once per staging buffer, so that every later step is copy -> replay -> loss read
                     if (i == 0 and stage_graphs is None and capturable and not nums and niters - done >= _HOST_GRAPH_MIN_ITERS
