@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   4
+#define PINN_ABI_VERSION   5
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -108,7 +108,8 @@ typedef struct PinnColumn {
  * Network (reference ConvBlockModel.forward model_torch.py:170-172, layouts 'fa…f'):
  *   n_layers linear layers, widths[0] = ndims + nparams, widths[n_layers] = 1;
  *   act[l] is the activation applied AFTER linear layer l (0-based); act[n_layers-1] must
- *   be PINN_ACT_NONE.
+ *   be PINN_ACT_NONE.  skip_src[l] = s >= 0 adds the output of layer s (after ITS activation and skip)
+ *   to the activated output of layer l (residual connections 'R … +').
  * Flat parameter buffer (fp32): for layer l the weight matrix [widths[l+1] x widths[l]]
  *   row-major (== torch nn.Linear.weight) at w_off[l] and the bias at b_off[l]; the scalar
  *   log_scale (model_torch.py:50) at log_scale_off; equation variables (V token,
@@ -138,6 +139,8 @@ typedef struct PinnSpec {
     int32_t  n_layers;
     int32_t  widths[PINN_MAX_LAYERS + 1];
     int32_t  act[PINN_MAX_LAYERS];
+    int32_t  skip_src[PINN_MAX_LAYERS];   /* -1, or the earlier layer whose (activated) output is added to this
+                                             layer's activated output: layouts 'faR fa fa+ f' (model_torch.py:142-156) */
     int32_t  w_off[PINN_MAX_LAYERS];
     int32_t  b_off[PINN_MAX_LAYERS];
     int32_t  n_params;

@@ -44,7 +44,7 @@ class Problem:
 
     def __init__(self, equation, ndims, nparams=0, initial_condition=None, boundary_condition=None,
                  domain=(0.0, 1.0), features=(20, 30, 1), activation='Sigmoid', dtype=torch.float32,
-                 variables=None, seed=0):
+                 variables=None, seed=0, layout=None):
         self.equation = equation
         self.ndims, self.nparams = ndims, nparams
         self.total = ndims + nparams
@@ -58,6 +58,8 @@ class Problem:
         self.dtype = dtype
         self.activation = activation
         self.features = list(features)
+        # batchflow layout letters: f dense, a activation, R save tensor, + add it back (model_torch.py:142-156)
+        self.layout = (layout or 'fa' * (len(self.features) - 1) + 'f').replace(' ', '')
         gen = torch.Generator().manual_seed(seed)
         self.weights, self.biases = [], []
         n_in = self.total
@@ -116,11 +118,17 @@ class Problem:
     def net(self, xs_concat):
         h = xs_concat
         act = getattr(torch.nn, self.activation)()
-        last = len(self.weights) - 1
-        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
-            h = torch.nn.functional.linear(h, w, b)
-            if i != last:
+        saved, i_f = [], 0
+        for letter in self.layout:
+            if letter == 'f':
+                h = torch.nn.functional.linear(h, self.weights[i_f], self.biases[i_f])
+                i_f += 1
+            elif letter == 'a':
                 h = act(h)
+            elif letter == 'R':
+                saved.append(h)
+            elif letter == '+':
+                h = h + saved.pop()
         return h
 
     def ansatz(self, u, xs_concat):

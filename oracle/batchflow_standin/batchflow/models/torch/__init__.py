@@ -1,4 +1,4 @@
-""" Stand-in for `batchflow.models.torch.Block`, restricted to dense layouts ('f', 'a').
+""" Stand-in for `batchflow.models.torch.Block`, restricted to dense layouts ('f', 'a', 'R', '+').
 
 Call site being served: pydens/model_torch.py:164-168
     Block(inputs=fake_inputs, layout=..., features=[...], activation=..., **user_kwargs)
@@ -31,9 +31,20 @@ class Block(nn.Module):
                 act = acts[i_a]
                 i_a += 1
                 layers.append(getattr(nn, act)() if isinstance(act, str) else act())
+            elif letter in 'R+':                      # residual: R saves the tensor, + adds it back
+                layers.append(nn.Identity())
             else:
                 raise ValueError('stand-in Block supports only dense layouts, got %r' % letter)
-        self.layers = nn.Sequential(*layers)
+        self.layers = nn.ModuleList(layers)
+        self.letters = layout
 
     def forward(self, x):
-        return self.layers(x)
+        saved = []
+        for letter, layer in zip(self.letters, self.layers):
+            if letter == 'R':
+                saved.append(x)
+            elif letter == '+':
+                x = x + saved.pop()
+            else:
+                x = layer(x)
+        return x

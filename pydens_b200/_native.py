@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3}
@@ -29,6 +29,7 @@ class PinnSpec(C.Structure):
         ('n_layers', C.c_int32),
         ('widths', C.c_int32 * (MAX_LAYERS + 1)),
         ('act', C.c_int32 * MAX_LAYERS),
+        ('skip_src', C.c_int32 * MAX_LAYERS),
         ('w_off', C.c_int32 * MAX_LAYERS),
         ('b_off', C.c_int32 * MAX_LAYERS),
         ('n_params', C.c_int32),
@@ -132,7 +133,7 @@ def make_columns(cols, total):
 
 
 def build_spec(widths, acts, ndims, nparams, has_bc, bc_value, has_ic, domain, traced, var_offsets=None,
-               w_off=None, b_off=None, log_scale_off=None, n_params=None):
+               w_off=None, b_off=None, log_scale_off=None, n_params=None, skips=None):
     """ Assemble a PinnSpec.
 
     widths: [total, n_1, ..., 1]; acts: activation name per linear layer ('none' for the last);
@@ -149,6 +150,7 @@ def build_spec(widths, acts, ndims, nparams, has_bc, bc_value, has_ic, domain, t
     for l in range(n_layers):
         s.widths[l] = widths[l]
         s.act[l] = ACT[acts[l]]
+        s.skip_src[l] = -1 if not skips or skips[l] is None else int(skips[l])
         if w_off is None:
             s.w_off[l] = off
             off += widths[l] * widths[l + 1]

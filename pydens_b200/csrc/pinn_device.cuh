@@ -39,8 +39,11 @@ struct DevLayer {
     int w_s;                    // smem float offset of W  [n_out_p4][n_in_p8] (reverse layout)
     int b_s;                    // smem float offset of bias [n_out_p4]
     int n_out_p4, n_in_p8;
-    int unit_base;              // first unit index of this layer's output buffer
-    int pad_;
+    int unit_base;              // first unit index of this layer's output buffer (stored jet, later its adjoint)
+    int post_base;              // residual layers: unit index of the buffer holding the activated output + skip, else -1
+    int skip_src;               // layer whose output is added to this layer's activated output, or -1
+    int adj_from;               // this layer feeds the skip of layer `adj_from` (whose post buffer carries the adjoint), or -1
+    int pad_[2];
 };
 
 struct alignas(16) DevPlan {
@@ -325,6 +328,38 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
         else if (NBMAX >= 2 && nb == 2) PINN_FWD_CASE(2)
         else PINN_FWD_CASE(1)
 #undef PINN_FWD_CASE
+    }
+}
+
+// Where a consumer reads the (activated) output of layer p: a residual layer keeps the sum
+// act(z_p) + skip in its post buffer, which reads back like the output of an identity activation;
+// any other layer is rebuilt from its stored jet with its own activation.
+PINN_HD const float* layer_output(const DevPlan& P, int p, const float* __restrict__ units, int C, int RS,
+                                  int& act_id) {
+    const DevLayer& Lp = P.layer[p];
+    if (Lp.post_base >= 0) { act_id = PINN_ACT_NONE; return units + (size_t)Lp.post_base * C * RS; }
+    act_id = Lp.act;
+    return units + (size_t)Lp.unit_base * C * RS;
+}
+
+// Residual layer l ('… R … fa+'): post buffer <- act-jet(stored jet of l) + output of layer skip_src.
+template <int NF, int NS>
+PINN_HD void skip_sum_pass(const DevPlan& P, int l, float* __restrict__ units, int RS) {
+    constexpr int C = 1 + NF + NS;
+    const DevLayer& L = P.layer[l];
+    const ActC own = make_actc(L.act);
+    int src_act;
+    const float* src_rows = layer_output(P, L.skip_src, units, C, RS, src_act);
+    const ActC srcc = make_actc(src_act);
+    const float* pre_rows = units + (size_t)L.unit_base * C * RS;
+    float* post_rows = units + (size_t)L.post_base * C * RS;
+#pragma unroll 1
+    for (int j = 0; j < L.n_out; ++j) {
+        float a[C], b[C];
+        load_post_jet<NF, NS>(pre_rows + (size_t)j * C * RS, RS, own, a);
+        load_post_jet<NF, NS>(src_rows + (size_t)j * C * RS, RS, srcc, b);
+#pragma unroll
+        for (int c = 0; c < C; ++c) post_rows[((size_t)j * C + c) * RS] = a[c] + b[c];
     }
 }
 
@@ -632,14 +667,19 @@ struct GradSink {
 // JJ = output units per reduction batch (4 normally, 1 for the single-output top layer).
 // No guards in the inner loops: rows/columns past the end are read from clamped (valid) addresses,
 // meet zero-padded weights, and their reduction entries are dropped at the sink.
-template <int NF, int NS, int JJ>
+template <int NF, int NS, int JJ, bool SKIP>
 PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restrict__ sw,
                        const float* __restrict__ out_rows, float* __restrict__ in_rows, int RS,
-                       const GradSink& sink) {
+                       const GradSink& sink,
+                       const float* __restrict__ load_rows, int load_act_id,
+                       const float* __restrict__ adj_in /* stashed skip adjoint to add, or null */,
+                       float* __restrict__ adj_out /* where to stash the adjoint of a residual layer, or null */) {
     constexpr int C = 1 + NF + NS;
     constexpr int JB = 8;
     const float* W = sw + L.w_s;
     const ActC below = make_actc(below_act_id);
+    const ActC load_act = make_actc(SKIP ? load_act_id : below_act_id);
+    if (!SKIP) load_rows = in_rows;
     const int n_cols = L.n_in + 1;                        // + bias column
 #pragma unroll 1
     for (int m0 = 0; m0 < n_cols; m0 += JB) {
@@ -648,7 +688,7 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
         for (int mm = 0; mm < JB; ++mm) {
             const int m = m0 + mm;
             const int mc = m < L.n_in ? m : L.n_in - 1;
-            load_post_jet<NF, NS>(in_rows + (size_t)mc * C * RS, RS, below, post[mm]);
+            load_post_jet<NF, NS>(load_rows + (size_t)mc * C * RS, RS, load_act, post[mm]);
             if (m == L.n_in) {                            // bias column: jet (1, 0, …, 0)
                 post[mm][0] = 1.0f;
 #pragma unroll
@@ -660,6 +700,14 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
         for (int mm = 0; mm < JB; ++mm)
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[mm][c] = 0.0f;
+        if (SKIP && adj_in) {                             // the layer below also feeds a skip connection
+#pragma unroll
+            for (int mm = 0; mm < JB; ++mm) {
+                const int mc = m0 + mm < L.n_in ? m0 + mm : L.n_in - 1;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[mm][c] = adj_in[((size_t)mc * C + c) * RS];
+            }
+        }
 
 #pragma unroll 1
         for (int j0 = 0; j0 < L.n_out; j0 += JJ) {
@@ -706,6 +754,12 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
 #pragma unroll
             for (int c = 0; c < C; ++c)
                 if (ok) row[(size_t)c * RS] = zb[c];
+            if (SKIP && adj_out) {                        // residual layer: its skip source needs this adjoint too
+                float* srow = adj_out + (size_t)(ok ? m0 + mm : 0) * C * RS;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (ok) srow[(size_t)c * RS] = acc[mm][c];
+            }
         }
     }
 }
@@ -788,16 +842,17 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
 #pragma unroll 1
     for (int l = 0; l + 1 < Ln; ++l) {
         const DevLayer& L = P.layer[l];
-        const float* in_rows = (l == 0) ? coords : units + (size_t)P.layer[l - 1].unit_base * C * RS;
-        int in_act = (l == 0) ? PINN_ACT_NONE : P.layer[l - 1].act;
+        int in_act = PINN_ACT_NONE;
+        const float* in_rows = (l == 0) ? coords : layer_output(P, l - 1, units, C, RS, in_act);
         fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, P.dir_col,
                               units + (size_t)L.unit_base * C * RS, RS);
+        if (L.skip_src >= 0) skip_sum_pass<NF, NS>(P, l, units, RS);
     }
     float N[C];
     {
         const DevLayer& L = P.layer[Ln - 1];
-        const float* in_rows = (Ln == 1) ? coords : units + (size_t)P.layer[Ln - 2].unit_base * C * RS;
-        int in_act = (Ln == 1) ? PINN_ACT_NONE : P.layer[Ln - 2].act;
+        int in_act = PINN_ACT_NONE;
+        const float* in_rows = (Ln == 1) ? coords : layer_output(P, Ln - 2, units, C, RS, in_act);
         fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, P.dir_col, RS, N);
     }
 
@@ -851,9 +906,19 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
     for (int l = Ln - 1; l >= 1; --l) {
         const DevLayer& L = P.layer[l];
         float* out_rows = units + (size_t)L.unit_base * C * RS;
-        float* in_rows = units + (size_t)P.layer[l - 1].unit_base * C * RS;
-        if (L.n_out == 1) bwd_layer<NF, NS, 1>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
-        else              bwd_layer<NF, NS, 4>(L, P.layer[l - 1].act, sw, out_rows, in_rows, RS, sink);
+        const DevLayer& B = P.layer[l - 1];                 // the layer below
+        float* in_rows = units + (size_t)B.unit_base * C * RS;
+        int load_act;
+        const float* load_rows = layer_output(P, l - 1, units, C, RS, load_act);
+        const float* adj_in = B.adj_from >= 0 ? units + (size_t)P.layer[B.adj_from].post_base * C * RS : nullptr;
+        float* adj_out = B.skip_src >= 0 ? units + (size_t)B.post_base * C * RS : nullptr;
+        if (B.post_base >= 0 || B.adj_from >= 0) {          // residual wiring around the layer below (rare path)
+            if (L.n_out == 1) bwd_layer<NF, NS, 1, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
+            else              bwd_layer<NF, NS, 4, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
+        } else {
+            if (L.n_out == 1) bwd_layer<NF, NS, 1, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr);
+            else              bwd_layer<NF, NS, 4, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr);
+        }
     }
     {
         const DevLayer& L = P.layer[0];
@@ -874,15 +939,16 @@ PINN_HD float point_forward(const DevPlan& P, const float* __restrict__ sw, cons
     int dummy_dir[1] = {0};
     for (int l = 0; l + 1 < Ln; ++l) {
         const DevLayer& L = P.layer[l];
-        const float* in_rows = (l == 0) ? coords : units + (size_t)P.layer[l - 1].unit_base * RS;
-        int in_act = (l == 0) ? PINN_ACT_NONE : P.layer[l - 1].act;
+        int in_act = PINN_ACT_NONE;
+        const float* in_rows = (l == 0) ? coords : layer_output(P, l - 1, units, 1, RS, in_act);
         fwd_layer<0, 0, JF>(L, sw, in_rows, l == 0, in_act, dummy_dir, units + (size_t)L.unit_base * RS, RS);
+        if (L.skip_src >= 0) skip_sum_pass<0, 0>(P, l, units, RS);
     }
     float N[1];
     {
         const DevLayer& L = P.layer[Ln - 1];
-        const float* in_rows = (Ln == 1) ? coords : units + (size_t)P.layer[Ln - 2].unit_base * RS;
-        int in_act = (Ln == 1) ? PINN_ACT_NONE : P.layer[Ln - 2].act;
+        int in_act = PINN_ACT_NONE;
+        const float* in_rows = (Ln == 1) ? coords : layer_output(P, Ln - 2, units, 1, RS, in_act);
         fwd_final<0, 0>(L, sw, in_rows, Ln == 1, in_act, dummy_dir, RS, N);
     }
     float icj[1] = {0.0f};

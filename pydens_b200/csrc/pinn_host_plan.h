@@ -103,6 +103,18 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
         L.w_s = sw;  sw += L.n_out_p4 * L.n_in_p8;
         L.b_s = sw;  sw += L.n_out_p4;
         L.unit_base = units; units += L.n_out;
+        L.post_base = -1; L.skip_src = -1; L.adj_from = -1;
+    }
+    for (int l = 0; l < Ln; ++l) {
+        const int src = s->skip_src[l];
+        if (src < 0) continue;
+        DevLayer& L = h.layer[l];
+        if (l == Ln - 1) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "skip connection into the output layer");
+        if (src >= l) PINN_PLAN_FAIL(PINN_E_INVALID, "skip_src[%d] = %d must be an earlier layer", l, src);
+        if (h.layer[src].n_out != L.n_out) PINN_PLAN_FAIL(PINN_E_INVALID, "skip %d -> %d: widths %d and %d differ", src, l, h.layer[src].n_out, L.n_out);
+        if (h.layer[src].adj_from >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "layer %d is the source of two skip connections", src);
+        L.skip_src = src; L.post_base = units; units += L.n_out;
+        h.layer[src].adj_from = l;
     }
     h.weights_floats = round_up_i(sw, 4);
     h.n_units = units;

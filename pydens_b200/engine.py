@@ -47,7 +47,7 @@ class FusedEngine:
         # ---- canonical flat layout: W_0, b_0, ..., log_scale, equation variables, everything else ----
         entries, off = [], 0
         w_off, b_off = [], []
-        for lin, _ in chain:
+        for lin, _, _ in chain:
             w_off.append(off); entries.append((lin.weight, off)); off += lin.weight.numel()
             b_off.append(off); entries.append((lin.bias, off)); off += lin.bias.numel()
         log_scale_off = off
@@ -72,14 +72,15 @@ class FusedEngine:
                 p.data = self.flat[o:o + n].view(p.shape)
                 p.grad = self.out[o:o + n].view(p.shape)
 
-        widths = [model.total] + [lin.out_features for lin, _ in chain]
-        acts = [act for _, act in chain]
+        widths = [model.total] + [c[0].out_features for c in chain]
+        acts = [c[1] for c in chain]
+        skips = [c[2] for c in chain]
         has_bc = model.boundary_condition is not None
         has_ic = model.raw_initial_condition is not None
         self.spec = _native.build_spec(widths, acts, model.ndims, model.nparams, has_bc,
                                        model.boundary_condition if has_bc else 0.0, has_ic, model.domain, traced,
                                        var_offsets=var_offsets, w_off=w_off, b_off=b_off,
-                                       log_scale_off=log_scale_off, n_params=self.n_params)
+                                       log_scale_off=log_scale_off, n_params=self.n_params, skips=skips)
         plan = C.c_void_p()
         _native.check(self.lib.pinn_plan_create(C.byref(self.spec), self.device.index, C.byref(plan)))
         self.plan = plan

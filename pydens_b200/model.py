@@ -173,25 +173,45 @@ class DenseBlock(nn.Module):
         return x
 
     def dense_chain(self):
-        """ [(linear, activation-name or 'none'), …] if the block is a plain f/a chain the fused kernel
-        covers, else None. """
-        chain = []
+        """ [(linear, activation-name or 'none', skip_src or None), …] if the block is a dense chain the fused
+        kernel covers, else None.  Residual connections are covered in their usual form — both 'R' and '+'
+        directly after an activation ('faR fa fa+ f'): `skip_src` is the index of the dense layer whose
+        activated output is added to this layer's activated output. """
+        chain, stack = [], []
         kinds, ops = self.kinds, list(self.ops)
         i = 0
         while i < len(kinds):
-            if kinds[i] != 'f':
-                return None
-            act = 'none'
-            if i + 1 < len(kinds) and kinds[i + 1] == 'a':
-                mod = ops[i + 1]
-                name = type(mod).__name__.lower()
-                if name not in _ACT_NAMES:
-                    return None
-                act = _ACT_NAMES[name]
+            kind = kinds[i]
+            if kind == 'f':
+                lin, act = ops[i], 'none'
                 i += 1
-            chain.append((ops[i - 1] if act != 'none' else ops[i], act))
-            i += 1
-        return chain
+                if i < len(kinds) and kinds[i] == 'a':
+                    name = type(ops[i]).__name__.lower()
+                    if name not in _ACT_NAMES:
+                        return None
+                    act = _ACT_NAMES[name]
+                    i += 1
+                chain.append([lin, act, None])
+            elif kind in 'R+':
+                if not chain or kinds[i - 1] not in ('a', '+') or (kind == '+' and kinds[i - 1] != 'a'):
+                    return None                       # skip from the raw input / around a bare dense layer
+                if kind == 'R':
+                    stack.append(len(chain) - 1)      # saves the layer's final output (activation + its own skip)
+                else:
+                    if not stack or chain[-1][2] is not None:
+                        return None
+                    src = stack.pop()
+                    if src == len(chain) - 1 or chain[src][0].out_features != chain[-1][0].out_features:
+                        return None
+                    if any(c[2] == src for c in chain):
+                        return None                   # one consumer per saved tensor
+                    chain[-1][2] = src
+                i += 1
+            else:
+                return None
+        if stack:
+            return None
+        return [tuple(c) for c in chain]
 
 
 class ConvBlockModel(TorchModel):

@@ -115,7 +115,9 @@ class Solver:
                 raise tracer.NotLowerable('layout %r is not a plain dense chain' % model.conv_block.layout)
             if chain[-1][1] != 'none' or chain[-1][0].out_features != 1:
                 raise tracer.NotLowerable('network must end with a dense layer of one unit')
-            if any(lin.bias is None for lin, _ in chain) or len(chain) > _native.MAX_LAYERS:
+            if chain[-1][2] is not None:
+                raise tracer.NotLowerable('skip connection into the output layer')
+            if any(c[0].bias is None for c in chain) or len(chain) > _native.MAX_LAYERS:
                 raise tracer.NotLowerable('unsupported dense layers')
             if model.total > _native.MAX_DIMS:
                 raise tracer.NotLowerable('more than %d point columns' % _native.MAX_DIMS)

@@ -44,12 +44,12 @@ def spec_for(name):
     total = cfg['ndims'] + cfg['nparams']
     tr = traced_problem(name)
     widths = [total] + list(cfg['features'])
-    acts = [cfg['activation'].lower()] * (len(widths) - 2) + ['none']
+    acts, skips = P.layer_plan(name)
     dom = cfg['domain']
     if isinstance(dom[0], (int, float)):
         dom = [tuple(dom)] * cfg['ndims']
     return N.build_spec(widths, acts, cfg['ndims'], cfg['nparams'], cfg['bc'] is not None,
-                        cfg['bc'] if cfg['bc'] is not None else 0.0, P.has_ic(name), dom, tr)
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, P.has_ic(name), dom, tr, skips=skips)
 
 
 def emul_step(spec, params, points):

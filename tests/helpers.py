@@ -21,7 +21,7 @@ def oracle_problem(name, dtype=torch.float32, params=None):
     prob = ap.Problem(lambda u, *xs, D, V: cfg['equation'](u, *xs, D=D, V=V),
                       ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=ic,
                       boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
-                      activation=cfg['activation'], dtype=dtype, variables=cfg.get('variables'))
+                      activation=cfg['activation'], dtype=dtype, variables=cfg.get('variables'), layout=cfg['layout'])
     holder['prob'] = prob
     if params is not None:
         prob.load_flat(torch.as_tensor(params))

@@ -60,6 +60,14 @@ def _icf_heat1d(V):                                  # README.md:112-118 style: 
     return lambda x: V('amp', 0.7) * torch.sin(PI * x) + V('shift', 0.2) ** 2
 
 
+def _heat1d(f, x, t, D, V):
+    return D(D(f, x), x) - D(f, t)
+
+
+def _ic_sin(x):
+    return torch.sin(PI * x)
+
+
 def _ic_heat(x, y):
     return 10 * x * y * (1 - x) * (1 - y)
 
@@ -100,16 +108,22 @@ PROBLEMS = {
     'heat1d_icvar': dict(equation=_heat1d_icvar, ndims=2, nparams=0, ic=None, ic_factory=_icf_heat1d, bc=0.0,
                          domain=(0, 1), features=[9, 7, 1], activation='Tanh', layout='fafaf',
                          variables={'amp': 0.7, 'shift': 0.2, 'src': 0.1}, ranges=[(0, 1), (0, 1)], log_scale=-0.2),
+    # residual layouts (reference docstring model_torch.py:142-156: 'faR fa fa+ f')
+    'poisson_skip': dict(equation=_poisson2d, ndims=2, nparams=0, ic=None, bc=1, domain=(0, 1),
+                         features=[8, 6, 8, 1], activation='Tanh', layout='faR fa fa+ f', ranges=[(0, 1), (0, 1)]),
+    'heat_resnet': dict(equation=_heat1d, ndims=2, nparams=0, ic=_ic_sin, bc=0, domain=(0, 1),
+                        features=[7, 7, 7, 1], activation='Sigmoid', layout='fa R fa+ R fa+ f',
+                        ranges=[(0, 1), (0, 1)], log_scale=0.1),
     'nonlinear': dict(equation=_nonlinear, ndims=2, nparams=0, ic=None, bc=None, domain=(0, 1),
                       features=[7, 5, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1), (0, 1)]),
 }
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
-                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90}
+                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
-               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02)}
+               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01)}
 
 
 def make_points(name, batch, seed):
@@ -118,6 +132,22 @@ def make_points(name, batch, seed):
     rng = np.random.RandomState(seed)
     cols = [rng.uniform(lo, hi, size=(batch, 1)) for lo, hi in cfg['ranges']]
     return np.concatenate(cols, axis=1).astype(np.float32)
+
+
+def layer_plan(name):
+    """ (activation per dense layer, skip source per dense layer) parsed from the layout string. """
+    cfg = PROBLEMS[name]
+    acts, skips, stack = [], [], []
+    for letter in cfg['layout'].replace(' ', ''):
+        if letter == 'f':
+            acts.append('none'); skips.append(None)
+        elif letter == 'a':
+            acts[-1] = cfg['activation'].lower()
+        elif letter == 'R':
+            stack.append(len(acts) - 1)
+        elif letter == '+':
+            skips[-1] = stack.pop()
+    return acts, skips
 
 
 def make_ic(name, V):

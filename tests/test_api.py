@@ -84,8 +84,15 @@ def test_lowering_decisions():
     assert s._traced is not None and s._traced.var_names == ['init'] and s._traced.ic_has_vars
     s.fit(niters=2, batch_size=8)                                 # (CPU here: autograd path)
     s = Solver(pde, ndims=2, layout='faR fa+ f', features=[6, 6, 1], device='cpu')
+    assert s._traced is not None and [c[2] for c in s._chain] == [None, 0, None]     # residual layouts lower
+    s.fit(niters=2, batch_size=8)
+    s = Solver(pde, ndims=2, layout='fa R fa+ R fa+ f', features=[5, 5, 5, 1], device='cpu')
+    assert [c[2] for c in s._chain] == [None, 0, 1, None]                           # chained residual blocks
+    s = Solver(pde, ndims=2, layout='R fa fa + f', features=[2, 2, 1], device='cpu')   # skip from the raw input
     assert s._traced is None and 'dense chain' in s._lower_error
     s.fit(niters=2, batch_size=8)
+    s = Solver(pde, ndims=2, layout='fa fa f', features=[4, 4, 1], activation='Sin', device='cpu')
+    assert s._traced is None
 
     class MyModel(ConvBlockModel):
         def forward(self, xs):
