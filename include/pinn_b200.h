@@ -13,8 +13,9 @@
  *     (PyTorch tensors), borrowed for the duration of the call, 16-byte aligned.
  *   - All calls are stream-ordered on `stream` (a cudaStream_t passed as void*), perform
  *     no allocation and no host synchronisation, and are CUDA-graph capturable
- *     (pinn_plan_create / pinn_plan_destroy excepted: they allocate a small device copy of
- *     the plan and must not be called during capture).
+ *     (pinn_plan_create / pinn_plan_destroy excepted: they query the device and set kernel
+ *     attributes and must not be called during capture).  The plan travels to the kernels as a
+ *     __grid_constant__ parameter: there is no device-side plan object to keep alive.
  *   - Return value: 0 on success, negative PINN_E_* on failure; pinn_last_error() gives a
  *     thread-local human readable message.
  *   - A plan is immutable after creation and may be used from several streams.
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   5
+#define PINN_ABI_VERSION   6
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -123,9 +124,11 @@ typedef struct PinnColumn {
  *           t = column ndims-1, t0 = dom_lo[ndims-1], ic given by ic_prog.
  *
  * Jet set (what the nested D() calls of the equation need, model_torch.py:174-178):
- *   nf first-order directions; direction d differentiates along point column dir_col[d];
- *   the first ns (<= nf) of them additionally carry the second derivative along the same
- *   column.  Channel order of every jet: [value, d/dx_dir0.., d2/dx_dir0^2 ..].
+ *   nf first-order directions; direction d is the vector dir_vec[d][0..ndims+nparams) in point-column
+ *   space (dir_col[d] = k >= 0 when it is the unit vector of column k, else -1); the first ns (<= nf)
+ *   of them additionally carry the second directional derivative along the same vector.  Mixed
+ *   derivatives d2u/dx_i dx_j are obtained by polarisation from the direction e_i + e_j:
+ *   u_ij = (u_vv - u_ii - u_jj) / 2.  Channel order of every jet: [value, D_dir0.., D^2_dir0 ..].
  *
  * Programs: scratch slots 0..C-1 (C = 1 + nf + ns) are preloaded with the jet of u before
  *   eq_prog runs.  eq_out[0] is the slot of the residual r, eq_out[1+c] the slot of
@@ -155,6 +158,7 @@ typedef struct PinnSpec {
 
     int32_t  nf, ns;
     int32_t  dir_col[PINN_MAX_DIRS];
+    float    dir_vec[PINN_MAX_DIRS][PINN_MAX_DIMS];
 
     int32_t   n_eq;
     PinnInstr eq_prog[PINN_MAX_PROG];

@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3}
@@ -42,6 +42,7 @@ class PinnSpec(C.Structure):
         ('dom_lo', C.c_float * MAX_DIMS), ('dom_hi', C.c_float * MAX_DIMS),
         ('nf', C.c_int32), ('ns', C.c_int32),
         ('dir_col', C.c_int32 * MAX_DIRS),
+        ('dir_vec', (C.c_float * MAX_DIMS) * MAX_DIRS),
         ('n_eq', C.c_int32),
         ('eq_prog', PinnInstr * MAX_PROG),
         ('eq_out', C.c_int32 * (1 + 1 + 2 * MAX_DIRS + MAX_VARS)),
@@ -178,8 +179,10 @@ def build_spec(widths, acts, ndims, nparams, has_bc, bc_value, has_ic, domain, t
     for i in range(ndims):
         s.dom_lo[i], s.dom_hi[i] = float(domain[i][0]), float(domain[i][1])
     s.nf, s.ns = traced.nf, traced.ns
-    for d, col in enumerate(traced.dirs):
-        s.dir_col[d] = col
+    for d, vec in enumerate(traced.dir_vecs):
+        s.dir_col[d] = traced.dirs[d]
+        for k, v in enumerate(vec):
+            s.dir_vec[d][k] = float(v)
     fill_program(s.eq_prog, traced.eq_prog)
     s.n_eq = len(traced.eq_prog)
     for i, slot in enumerate(traced.eq_prog.outs):

@@ -60,7 +60,8 @@ struct alignas(16) DevPlan {
     int n_units;
     float bc;
     float t0;
-    int dir_col[PINN_MAX_DIRS];
+    int dir_col[PINN_MAX_DIRS];                       // unit-vector directions: their column; else -1
+    float dir_vec[PINN_MAX_DIRS][PINN_MAX_DIMS];      // direction vectors in point-column space
     int var_off[PINN_MAX_VARS];
     float lo[PINN_MAX_DIMS], hi[PINN_MAX_DIMS], inv_w2[PINN_MAX_DIMS];
     int eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
@@ -243,11 +244,11 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
     }
 }
 
-// First layer: the input jet is (x_k, e_dir, 0), so value channel is a dot product with the
-// coordinates, first-order channels are single weight columns, second-order channels vanish.
+// First layer: the input jet is (x_k, v_dir[k], 0): value channel is a dot product with the coordinates,
+// first-order channels are the same dot product with the direction vectors, second-order channels vanish.
 template <int NF, int NS, int NB>
 PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
-                             int n_in, const float* __restrict__ coords, int RS, const int* __restrict__ dir_col,
+                             int n_in, const float* __restrict__ coords, int RS, const float* __restrict__ dirv,
                              float (&acc)[NB * 4][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
@@ -259,6 +260,9 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
 #pragma unroll 1
     for (int k = 0; k < n_in; ++k) {
         float x = coords[(size_t)k * RS];
+        float vd[NF > 0 ? NF : 1];
+#pragma unroll
+        for (int d = 0; d < NF; ++d) vd[d] = dirv[d * PINN_MAX_DIMS + k];
         const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
 #pragma unroll
         for (int g = 0; g < NB; ++g) {
@@ -267,16 +271,13 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
             acc[4 * g + 1][0] = fmaf(w.y, x, acc[4 * g + 1][0]);
             acc[4 * g + 2][0] = fmaf(w.z, x, acc[4 * g + 2][0]);
             acc[4 * g + 3][0] = fmaf(w.w, x, acc[4 * g + 3][0]);
-        }
-    }
 #pragma unroll
-    for (int d = 0; d < NF; ++d) {
-        const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)dir_col[d] * wt_stride);
-#pragma unroll
-        for (int g = 0; g < NB; ++g) {
-            float4 w = wrow[g];
-            acc[4 * g + 0][1 + d] = w.x; acc[4 * g + 1][1 + d] = w.y;
-            acc[4 * g + 2][1 + d] = w.z; acc[4 * g + 3][1 + d] = w.w;
+            for (int d = 0; d < NF; ++d) {
+                acc[4 * g + 0][1 + d] = fmaf(w.x, vd[d], acc[4 * g + 0][1 + d]);
+                acc[4 * g + 1][1 + d] = fmaf(w.y, vd[d], acc[4 * g + 1][1 + d]);
+                acc[4 * g + 2][1 + d] = fmaf(w.z, vd[d], acc[4 * g + 2][1 + d]);
+                acc[4 * g + 3][1 + d] = fmaf(w.w, vd[d], acc[4 * g + 3][1 + d]);
+            }
         }
     }
 }
@@ -301,7 +302,7 @@ PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, 
 // One whole hidden (or input) linear layer, blocked over output units.
 template <int NF, int NS, int JF>
 PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
-                       bool in_is_coords, int in_act_id, const int* __restrict__ dir_col,
+                       bool in_is_coords, int in_act_id, const float* __restrict__ dirv,
                        float* __restrict__ out_rows, int RS) {
     constexpr int NBMAX = JF / 4;
     const float* Wt = sw + L.wt_s;
@@ -317,7 +318,7 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
             float acc[NB * 4][1 + NF + NS];                                                         \
             if (in_is_coords)                                                                       \
                 fwd_block_input<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,    \
-                                            dir_col, acc);                                          \
+                                            dirv, acc);                                             \
             else                                                                                    \
                 fwd_block_hidden<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,   \
                                              in_act, acc);                                          \
@@ -366,7 +367,7 @@ PINN_HD void skip_sum_pass(const DevPlan& P, int l, float* __restrict__ units, i
 // Final linear layer (one output unit, no activation): the network jet N lands in registers.
 template <int NF, int NS>
 PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
-                       bool in_is_coords, int in_act_id, const int* __restrict__ dir_col, int RS,
+                       bool in_is_coords, int in_act_id, const float* __restrict__ dirv, int RS,
                        float (&N)[1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
     const ActC in_act = make_actc(in_act_id);
@@ -375,9 +376,11 @@ PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const fl
 #pragma unroll
     for (int c = 1; c < C; ++c) N[c] = 0.0f;
     if (in_is_coords) {
-        for (int k = 0; k < L.n_in; ++k) N[0] = fmaf(w[k], in_rows[(size_t)k * RS], N[0]);
+        for (int k = 0; k < L.n_in; ++k) {
+            N[0] = fmaf(w[k], in_rows[(size_t)k * RS], N[0]);
 #pragma unroll
-        for (int d = 0; d < NF; ++d) N[1 + d] = w[dir_col[d]];
+            for (int d = 0; d < NF; ++d) N[1 + d] = fmaf(w[k], dirv[d * PINN_MAX_DIMS + k], N[1 + d]);
+        }
     } else {
 #pragma unroll 1
         for (int k = 0; k < L.n_in; ++k) {
@@ -469,18 +472,45 @@ PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, 
         st.G = G;
 #pragma unroll
         for (int d = 0; d < NF; ++d) {
-            int k = P.dir_col[d];
-            if (k < P.nsp) {
-                float others = 1.0f;
+            const int k = P.dir_col[d];
+            if (k >= 0) {                                 // unit vector of column k
+                if (k < P.nsp) {
+                    float others = 1.0f;
+                    for (int i = 0; i < P.nsp; ++i) {
+                        if (i != k) {
+                            float x = coords[(size_t)i * RS];
+                            others *= (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
+                        }
+                    }
+                    float xk = coords[(size_t)k * RS];
+                    st.Gd[d] = (P.lo[k] + P.hi[k] - 2.0f * xk) * P.inv_w2[k] * others;
+                    if (d < NS) st.Gdd[d] = -2.0f * P.inv_w2[k] * others;
+                }
+            } else {                                      // general direction v: sum_i v_i d_i G, sum_ij v_i v_j d_ij G
+                float gd = 0.0f, gdd = 0.0f;
                 for (int i = 0; i < P.nsp; ++i) {
-                    if (i != k) {
-                        float x = coords[(size_t)i * RS];
-                        others *= (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
+                    const float vi = P.dir_vec[d][i];
+                    if (vi == 0.0f) continue;
+                    const float xi = coords[(size_t)i * RS];
+                    const float gpi = (P.lo[i] + P.hi[i] - 2.0f * xi) * P.inv_w2[i];
+                    float others = 1.0f;
+                    for (int q = 0; q < P.nsp; ++q)
+                        if (q != i) { float x = coords[(size_t)q * RS]; others *= (x - P.lo[q]) * (P.hi[q] - x) * P.inv_w2[q]; }
+                    gd = fmaf(vi * gpi, others, gd);
+                    gdd = fmaf(vi * vi * (-2.0f * P.inv_w2[i]), others, gdd);
+                    for (int j = i + 1; j < P.nsp; ++j) {
+                        const float vj = P.dir_vec[d][j];
+                        if (vj == 0.0f) continue;
+                        const float xj = coords[(size_t)j * RS];
+                        const float gpj = (P.lo[j] + P.hi[j] - 2.0f * xj) * P.inv_w2[j];
+                        float rest = 1.0f;
+                        for (int q = 0; q < P.nsp; ++q)
+                            if (q != i && q != j) { float x = coords[(size_t)q * RS]; rest *= (x - P.lo[q]) * (P.hi[q] - x) * P.inv_w2[q]; }
+                        gdd = fmaf(2.0f * vi * vj * gpi * gpj, rest, gdd);
                     }
                 }
-                float xk = coords[(size_t)k * RS];
-                st.Gd[d] = (P.lo[k] + P.hi[k] - 2.0f * xk) * P.inv_w2[k] * others;
-                if (d < NS) st.Gdd[d] = -2.0f * P.inv_w2[k] * others;
+                st.Gd[d] = gd;
+                if (d < NS) st.Gdd[d] = gdd;
             }
         }
         st.v = fmaf(st.G, N[0], P.bc);
@@ -507,11 +537,11 @@ PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, 
         u[0] = fmaf(st.S, st.v, icj[0]);
 #pragma unroll
         for (int d = 0; d < NF; ++d) {
-            bool is_t = (P.dir_col[d] == P.ndims - 1);
-            float Sd = is_t ? st.S1 : 0.0f;
+            const float vt = P.dir_vec[d][P.ndims - 1];     // t-component of the direction
+            float Sd = vt * st.S1;
             u[1 + d] = fmaf(Sd, st.v, fmaf(st.S, st.vd[d], icj[1 + d]));
             if (d < NS) {
-                float Sdd = is_t ? st.S2 : 0.0f;
+                float Sdd = vt * vt * st.S2;
                 u[1 + NF + d] = fmaf(Sdd, st.v, fmaf(2.0f * Sd, st.vd[d], fmaf(st.S, st.vdd[d], icj[1 + NF + d])));
             }
         }
@@ -533,20 +563,21 @@ PINN_HD float ansatz_adjoint(const DevPlan& P, const AnsatzState<NF, NS>& st,
         vb = st.S * ub[0];
 #pragma unroll
         for (int d = 0; d < NF; ++d) {
-            bool is_t = (P.dir_col[d] == P.ndims - 1);
-            float Sd = is_t ? st.S1 : 0.0f;
+            const float vt = P.dir_vec[d][P.ndims - 1];
+            float Sd = vt * st.S1;
             vb = fmaf(Sd, ub[1 + d], vb);
             vdb[d] = st.S * ub[1 + d];
             Sb = fmaf(ub[1 + d], st.vd[d], Sb);
-            if (is_t) S1b = fmaf(ub[1 + d], st.v, S1b);
+            S1b = fmaf(vt * ub[1 + d], st.v, S1b);
             if (d < NS) {
-                float Sdd = is_t ? st.S2 : 0.0f;
+                float Sdd = vt * vt * st.S2;
                 float q = ub[1 + NF + d];
                 vb = fmaf(Sdd, q, vb);
                 vdb[d] = fmaf(2.0f * Sd, q, vdb[d]);
                 vddb[d] = st.S * q;
                 Sb = fmaf(q, st.vdd[d], Sb);
-                if (is_t) { S1b = fmaf(2.0f * q, st.vd[d], S1b); S2b = fmaf(q, st.v, S2b); }
+                S1b = fmaf(2.0f * vt * q, st.vd[d], S1b);
+                S2b = fmaf(vt * vt * q, st.v, S2b);
             }
         }
         // S = sig(w) - 1/2, S1 = sig'(w) e, S2 = sig''(w) e^2, w = (t - t0) e, e = exp(-s), dw/ds = -w
@@ -786,7 +817,7 @@ PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, in
 // in column n_in when n_in < PINN_MAX_DIMS.
 template <int NF, int NS>
 PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_rows,
-                               const float* __restrict__ coords, int RS, const int* __restrict__ dir_col,
+                               const float* __restrict__ coords, int RS, const float* __restrict__ dirv,
                                const GradSink& sink) {
     constexpr int C = 1 + NF + NS;
     float x[PINN_MAX_DIMS];
@@ -807,7 +838,7 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
             for (int m = 0; m < PINN_MAX_DIMS; ++m) {
                 float e = zb[0] * x[m];
 #pragma unroll
-                for (int d = 0; d < NF; ++d) e += (dir_col[d] == m) ? zb[1 + d] : 0.0f;
+                for (int d = 0; d < NF; ++d) e = fmaf(dirv[d * PINN_MAX_DIMS + m], zb[1 + d], e);
                 v[jj * PINN_MAX_DIMS + m] = e;
             }
         }
@@ -844,7 +875,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const DevLayer& L = P.layer[l];
         int in_act = PINN_ACT_NONE;
         const float* in_rows = (l == 0) ? coords : layer_output(P, l - 1, units, C, RS, in_act);
-        fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, P.dir_col,
+        fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, &P.dir_vec[0][0],
                               units + (size_t)L.unit_base * C * RS, RS);
         if (L.skip_src >= 0) skip_sum_pass<NF, NS>(P, l, units, RS);
     }
@@ -853,7 +884,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const DevLayer& L = P.layer[Ln - 1];
         int in_act = PINN_ACT_NONE;
         const float* in_rows = (Ln == 1) ? coords : layer_output(P, Ln - 2, units, C, RS, in_act);
-        fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, P.dir_col, RS, N);
+        fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, &P.dir_vec[0][0], RS, N);
     }
 
     // ---- ansatz + residual ----
@@ -923,7 +954,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
     {
         const DevLayer& L = P.layer[0];
         float* out_rows = units + (size_t)L.unit_base * C * RS;
-        wgrad_input_layer<NF, NS>(L, out_rows, coords, RS, P.dir_col, sink);
+        wgrad_input_layer<NF, NS>(L, out_rows, coords, RS, &P.dir_vec[0][0], sink);
     }
     return r;
 }
@@ -936,7 +967,7 @@ PINN_HD float point_forward(const DevPlan& P, const float* __restrict__ sw, cons
     float* coords = st;
     float* units = st + (size_t)P.row_units * RS;
     float* scr = st + (size_t)row_scr_fwd * RS;
-    int dummy_dir[1] = {0};
+    float dummy_dir[1] = {0.0f};
     for (int l = 0; l + 1 < Ln; ++l) {
         const DevLayer& L = P.layer[l];
         int in_act = PINN_ACT_NONE;

@@ -51,8 +51,18 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     if (s->nf < 0 || s->nf > PINN_MAX_DIRS || s->ns < 0 || s->ns > s->nf) PINN_PLAN_FAIL(PINN_E_INVALID, "jet set nf=%d ns=%d", s->nf, s->ns);
     if (s->n_vars < 0 || s->n_vars > PINN_MAX_VARS) PINN_PLAN_FAIL(PINN_E_INVALID, "n_vars");
     const int C = 1 + s->nf + s->ns;
-    for (int d = 0; d < s->nf; ++d)
-        if (s->dir_col[d] < 0 || s->dir_col[d] >= total) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_col[%d]", d);
+    for (int d = 0; d < s->nf; ++d) {
+        if (s->dir_col[d] >= total) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_col[%d]", d);
+        bool any = false;
+        for (int k = 0; k < total; ++k) {
+            const float v = s->dir_vec[d][k];
+            if (!(v == v) || v > 1e6f || v < -1e6f) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_vec[%d][%d]", d, k);
+            any = any || v != 0.0f;
+            if (s->dir_col[d] >= 0 && v != (k == s->dir_col[d] ? 1.0f : 0.0f))
+                PINN_PLAN_FAIL(PINN_E_INVALID, "dir_vec[%d] is not the unit vector of column %d", d, s->dir_col[d]);
+        }
+        if (!any) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_vec[%d] is zero", d);
+    }
     if (s->n_slots < C || s->n_slots > PINN_MAX_SLOTS) PINN_PLAN_FAIL(PINN_E_INVALID, "n_slots %d", s->n_slots);
     int rc;
     if ((rc = validate_prog(s->eq_prog, s->n_eq, s->n_slots, total, s->n_vars, "eq_prog", msg, msg_len))) return rc;
@@ -75,7 +85,10 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     h.bc = s->bc_value;
     h.ic_has_vars = (s->has_ic && s->ic_has_vars) ? 1 : 0;
     h.t0 = s->dom_lo[s->ndims - 1];
-    for (int d = 0; d < PINN_MAX_DIRS; ++d) h.dir_col[d] = d < s->nf ? s->dir_col[d] : 0;
+    for (int d = 0; d < PINN_MAX_DIRS; ++d) {
+        h.dir_col[d] = d < s->nf ? s->dir_col[d] : 0;
+        for (int k = 0; k < PINN_MAX_DIMS; ++k) h.dir_vec[d][k] = (d < s->nf && k < total) ? s->dir_vec[d][k] : 0.0f;
+    }
     for (int i = 0; i < PINN_MAX_VARS; ++i) h.var_off[i] = i < s->n_vars ? s->var_off[i] : 0;
     for (int i = 0; i < PINN_MAX_DIMS; ++i) {
         h.lo[i] = s->dom_lo[i]; h.hi[i] = s->dom_hi[i];

@@ -145,7 +145,15 @@ class Solver:
     def _get_engine(self):
         if self._engine is None:
             from .engine import FusedEngine
-            self._engine = FusedEngine(self)
+            try:
+                self._engine = FusedEngine(self)
+            except _native.NativeError as exc:
+                # the library understood the request but its kernels do not cover it (e.g. a network whose
+                # weights do not fit shared memory): that is a lowering failure, not a crash
+                if exc.code == _native.E_UNSUPPORTED and self.backend == 'auto':
+                    self._traced, self._lower_error = None, str(exc)
+                    return None
+                raise
         return self._engine
 
     def _fused_possible(self, criterion, loss_terms):
@@ -214,7 +222,10 @@ class Solver:
                 warnings.warn('pydens_b200: using the autograd path (%s)' % why, stacklevel=2)
                 self._warned = True
             return self._fit_autograd(niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs)
-        return self._get_engine().fit(niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs)
+        engine = self._get_engine()
+        if engine is None:                              # plan creation reported "unsupported": autograd path
+            return self.fit(niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs)
+        return engine.fit(niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs)
 
     def _make_optimizer(self, optimizer, lr, fused_hint=False, **kwargs):
         if optimizer is None:
@@ -285,8 +296,9 @@ class Solver:
         pts = self.reshape_and_concat(xs).to(self.device, torch.float32)
         self.model.eval()
         if self._traced is not None and self.backend != 'torch' and self.device.type == 'cuda':
-            out = self._get_engine().forward(pts)
-            return out.reshape(-1, 1).cpu().numpy()
+            engine = self._get_engine()
+            if engine is not None:
+                return engine.forward(pts).reshape(-1, 1).cpu().numpy()
         with torch.no_grad():
             result = self.ctx.run(self.model, pts)
         return result.detach().cpu().numpy()

@@ -60,6 +60,8 @@ class Expr:
             return 'u' + ''.join('_%d' % i for i in self.value)
         if self.kind == 'var':
             return 'V[%s]' % self.value
+        if self.kind == 'ch':
+            return 'U%d' % self.value
         if self.kind == 'powi':
             return '(%r)**%d' % (self.args[0], self.value)
         return '%s(%s)' % (self.kind, ', '.join(map(repr, self.args)))
@@ -89,6 +91,11 @@ def uleaf(multi_index=()):
 
 def var(name):
     return Expr('var', (), name)
+
+
+def chleaf(c):
+    """ Channel c of the jet of u as the kernel carries it (value, directional firsts, directional seconds). """
+    return Expr('ch', (), int(c))
 
 
 def add(a, b):
@@ -276,7 +283,7 @@ def diff_leaf(e, leaf, memo=None):
         return hit
     if e is leaf:
         r = ONE
-    elif e.kind in ('const', 'coord', 'u', 'var'):
+    elif e.kind in ('const', 'coord', 'u', 'var', 'ch'):
         r = ZERO
     else:
         r = _chain(e, lambda a: diff_leaf(a, leaf, memo))
@@ -295,6 +302,32 @@ def leaves(e, kinds, seen=None, out=None):
     for a in e.args:
         leaves(a, kinds, seen, out)
     return out
+
+
+_REBUILD = {'add': lambda a: add(*a), 'sub': lambda a: sub(*a), 'mul': lambda a: mul(*a), 'div': lambda a: div(*a),
+            'pow': lambda a: power(*a), 'neg': lambda a: neg(*a)}
+
+
+def substitute(e, mapping, memo=None):
+    """ Rebuild `e` with the leaves in `mapping` replaced by the mapped expressions. """
+    memo = {} if memo is None else memo
+    hit = memo.get(e)
+    if hit is not None:
+        return hit
+    if e in mapping:
+        r = mapping[e]
+    elif not e.args:
+        r = e
+    else:
+        args = [substitute(a, mapping, memo) for a in e.args]
+        if e.kind == 'powi':
+            r = powi(args[0], e.value)
+        elif e.kind in _REBUILD:
+            r = _REBUILD[e.kind](args)
+        else:
+            r = unary(e.kind, args[0])
+    memo[e] = r
+    return r
 
 
 # ------------------------------------------------------------------------------------------------
@@ -444,8 +477,8 @@ class Program:
 def lower(outputs, channel_of_u, var_index, n_reserved):
     """ Linearise `outputs` (list of Expr) into one program.
 
-    Slots [0, n_reserved) hold the jet of u on entry and are never written; `channel_of_u` maps a
-    'u' leaf to its reserved slot; `var_index` maps a variable name to its VAR operand.
+    Slots [0, n_reserved) hold the jet of u on entry and are never written ('ch' leaves read them;
+    `channel_of_u` is kept for the signature only); `var_index` maps a variable name to its VAR operand.
     """
     order, seen = [], set()
 
@@ -508,17 +541,17 @@ def lower(outputs, channel_of_u, var_index, n_reserved):
     for i, e in enumerate(order):
         if e not in needed:
             continue
-        if e.kind == 'u':
-            if e not in channel_of_u:
-                raise NotLowerable('unexpected derivative leaf %r' % e)
-            slot_of[e] = channel_of_u[e]
+        if e.kind == 'ch':
+            slot_of[e] = e.value
             continue
+        if e.kind == 'u':
+            raise NotLowerable('unexpected derivative leaf %r' % e)
         imm = immediate_form(e)
         operands = [imm[1]] if imm else list(e.args)
         srcs = [slot_of[a] for a in operands]
         # operands whose last use is this instruction free their slot (never a reserved/output one)
         for a in operands:
-            if last_use.get(a) == i and a.kind != 'u' and slot_of[a] >= n_reserved and slot_of[a] not in free:
+            if last_use.get(a) == i and a.kind != 'ch' and slot_of[a] >= n_reserved and slot_of[a] not in free:
                 free.append(slot_of[a])
         dst = alloc()
         slot_of[e] = dst
@@ -581,7 +614,8 @@ class TracedEquation:
 
     def __init__(self):
         self.residual = None        # Expr
-        self.dirs = []              # point columns of the first-order directions (second-order first)
+        self.dirs = []              # per direction: its point column when it is a unit vector, else -1
+        self.dir_vecs = []          # per direction: the vector in point-column space (second-order directions first)
         self.ns = 0                 # how many of them also carry a second derivative
         self.var_names = []         # variables used by the equation, in VAR-operand order
         self.eq_prog = None         # outputs: [r, dr/dchannel_0 .. dr/dchannel_{C-1}, dr/dV_0 ..]
@@ -614,27 +648,43 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
     T.residual = res
 
     u_leaves = leaves(res, ('u',))
-    first, second = set(), set()
+    first, second, mixed = set(), set(), set()
     for l in u_leaves:
         mi = l.value
         if len(mi) == 1:
             first.add(mi[0])
         elif len(mi) == 2:
             if mi[0] != mi[1]:
-                raise NotLowerable('mixed second derivatives are not supported by the fused path yet')
-            second.add(mi[0]); first.add(mi[0])
-    T.dirs = sorted(second) + sorted(first - second)
-    T.ns = len(second)
+                mixed.add(mi)                      # polarisation: u_ij = (u_vv - u_ii - u_jj) / 2, v = e_i + e_j
+                second.update(mi)
+            else:
+                second.add(mi[0])
+    first |= second
+    axes2, mixed, axes1 = sorted(second), sorted(mixed), sorted(first - second)
+
+    def unit(k, *more):
+        return [1.0 if i in (k,) + more else 0.0 for i in range(total)]
+    T.dir_vecs = [unit(k) for k in axes2] + [unit(i, j) for i, j in mixed] + [unit(k) for k in axes1]
+    T.dirs = list(axes2) + [-1] * len(mixed) + list(axes1)
+    T.ns = len(axes2) + len(mixed)
     nf, ns = len(T.dirs), T.ns
     if nf > 4:
         raise NotLowerable('more than 4 derivative directions')
     C = 1 + nf + ns
-    chan = {uleaf(): 0}
+    mapping = {uleaf(): chleaf(0)}
     for d, col in enumerate(T.dirs):
-        chan[uleaf((col,))] = 1 + d
-        if d < ns:
-            chan[uleaf((col, col))] = 1 + nf + d
-    by_channel = {v: k for k, v in chan.items()}
+        if col >= 0:
+            mapping[uleaf((col,))] = chleaf(1 + d)
+            if d < ns:
+                mapping[uleaf((col, col))] = chleaf(1 + nf + d)
+    for n, (i, j) in enumerate(mixed):
+        d = len(axes2) + n
+        mapping[uleaf((i, j))] = mul(const(0.5), sub(sub(chleaf(1 + nf + d), mapping[uleaf((i, i))]),
+                                                     mapping[uleaf((j, j))]))
+    res = substitute(res, mapping)
+    T.residual = res
+    chan = {}
+    by_channel = {c: chleaf(c) for c in range(C)}
 
     # the initial condition is traced first: its variables join the equation's (README.md:112-118)
     ic = None
@@ -657,10 +707,16 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
     T.n_slots = T.eq_prog.n_slots
 
     if ic is not None:
+        def along(e, vec):                         # directional derivative sum_k v_k d/dx_k
+            out = ZERO
+            for k, v in enumerate(vec):
+                if v != 0.0:
+                    out = add(out, mul(const(v), diff_coord(e, k)))
+            return out
         jet = [ic]
-        firsts = [diff_coord(ic, col) for col in T.dirs]
+        firsts = [along(ic, vec) for vec in T.dir_vecs]
         jet += firsts
-        jet += [diff_coord(firsts[d], T.dirs[d]) for d in range(ns)]
+        jet += [along(firsts[d], T.dir_vecs[d]) for d in range(ns)]
         T.ic_has_vars = bool(ic_vars)
         base = C
         if T.ic_has_vars:               # partials w.r.t. every variable; slots above the equation's

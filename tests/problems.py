@@ -60,6 +60,19 @@ def _icf_heat1d(V):                                  # README.md:112-118 style: 
     return lambda x: V('amp', 0.7) * torch.sin(PI * x) + V('shift', 0.2) ** 2
 
 
+def _mixed2d(f, x, y, D, V):                         # mixed second derivatives (both argument orders)
+    return (0.7 * D(D(f, x), y) + D(D(f, x), x) + 2 * D(D(f, y), y) - torch.sin(x * y)
+            + 0.1 * f * D(D(f, y), x))
+
+
+def _mixed_ic(f, x, y, t, D, V):
+    return D(f, t) - D(D(f, x), y) + 0.5 * D(f, x)
+
+
+def _ic_sincos(x, y):
+    return torch.sin(x) * torch.cos(2.0 * y)
+
+
 def _heat1d(f, x, t, D, V):
     return D(D(f, x), x) - D(f, t)
 
@@ -114,16 +127,22 @@ PROBLEMS = {
     'heat_resnet': dict(equation=_heat1d, ndims=2, nparams=0, ic=_ic_sin, bc=0, domain=(0, 1),
                         features=[7, 7, 7, 1], activation='Sigmoid', layout='fa R fa+ R fa+ f',
                         ranges=[(0, 1), (0, 1)], log_scale=0.1),
+    # mixed derivatives: carried by the extra direction e_x + e_y (polarisation)
+    'mixed2d': dict(equation=_mixed2d, ndims=2, nparams=0, ic=None, bc=0.3, domain=[(0, 2), (-1, 1)],
+                    features=[9, 8, 1], activation='Tanh', layout='fafaf', ranges=[(0, 2), (-1, 1)]),
+    'mixed_ic': dict(equation=_mixed_ic, ndims=3, nparams=0, ic=_ic_sincos, bc=0, domain=(0, 1),
+                     features=[10, 6, 1], activation='Sigmoid', layout='fafaf',
+                     ranges=[(0, 1), (0, 1), (0, 1)], log_scale=0.2),
     'nonlinear': dict(equation=_nonlinear, ndims=2, nparams=0, ic=None, bc=None, domain=(0, 1),
                       features=[7, 5, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1), (0, 1)]),
 }
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
-                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65}
+                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
-               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01)}
+               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01)}
 
 
 def make_points(name, batch, seed):

@@ -78,7 +78,9 @@ def test_variables_constraints_and_freezing():
 def test_lowering_decisions():
     assert Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu')._traced is None
     s = Solver(lambda f, x, y: D(D(f, x), y), ndims=2, device='cpu')
-    assert s._traced is None and 'mixed' in s._lower_error
+    assert s._traced is not None and s._traced.dirs == [0, 1, -1]                 # mixed derivative: polarised
+    s = Solver(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z), ndims=3, device='cpu')
+    assert s._traced is None and 'directions' in s._lower_error
     s = Solver(lambda f, t: D(f, t), ndims=1, initial_condition=lambda: V('init', data=torch.Tensor([3.0])),
                device='cpu')
     assert s._traced is not None and s._traced.var_names == ['init'] and s._traced.ic_has_vars

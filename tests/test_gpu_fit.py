@@ -118,3 +118,46 @@ def test_autograd_path_on_gpu_matches_fused_step():
     r = ref.ctx.run(ref.equation, u, *xs)
     l = torch.nn.functional.mse_loss(r, torch.zeros_like(r))
     assert abs(float(l) - loss) <= 1e-5 * abs(loss)
+
+
+def test_network_too_large_for_the_kernel_falls_back_loudly():
+    """ 300-wide layers: the weight matrices do not fit shared memory -> pinn_plan_create says
+    PINN_E_UNSUPPORTED; backend='auto' warns and trains on the autograd path, backend='fused' raises. """
+    from pydens_b200 import _native
+
+    def ode(f, x):
+        return D(f, x) - 2 * np.pi * torch.cos(2 * np.pi * x)
+    solver = Solver(ode, ndims=1, initial_condition=.5, layout='fafaf', features=[300, 300, 1], activation='Tanh')
+    with pytest.warns(UserWarning):
+        solver.fit(niters=3, batch_size=64)
+    assert len(solver.losses) == 3 and solver._engine is None
+    assert solver.predict(np.linspace(0, 1, 5)).shape == (5, 1)
+    strict = Solver(ode, ndims=1, initial_condition=.5, layout='fafaf', features=[300, 300, 1], activation='Tanh',
+                    backend='fused')
+    with pytest.raises(_native.NativeError):
+        strict.fit(niters=1, batch_size=8)
+
+
+def test_limits_eight_columns_and_deep_network():
+    """ PINN_MAX_DIMS point columns (bias of the first layer takes the separate path), 10 dense layers. """
+    def eq(f, x, y, z, t, a, b, c, d):
+        return D(D(f, x), x) + D(f, t) * a - b * c + d * D(f, y)
+    torch.manual_seed(3)
+    solver = Solver(eq, ndims=4, nparams=4, initial_condition=lambda x, y, z: x * y + z, boundary_condition=0.25,
+                    layout='fa' * 9 + 'f', features=[6, 7, 8, 9, 10, 9, 8, 7, 6, 1], activation='Tanh', backend='fused')
+    pts = torch.rand(1000, 8)
+    loss, grads, _ = solver.loss_and_grads(pts)
+    ref = Solver(eq, ndims=4, nparams=4, initial_condition=lambda x, y, z: x * y + z, boundary_condition=0.25,
+                 layout='fa' * 9 + 'f', features=[6, 7, 8, 9, 10, 9, 8, 7, 6, 1], activation='Tanh', backend='torch')
+    with torch.no_grad():
+        for a, b in zip(solver.model.conv_block.linears, ref.model.conv_block.linears):
+            b.weight.copy_(a.weight); b.bias.copy_(a.bias)
+    xs = [pts[:, i:i + 1].cuda().clone().requires_grad_() for i in range(8)]
+    u = ref.ctx.run(ref.model, ref.reshape_and_concat(xs))
+    r = ref.ctx.run(ref.equation, u, *xs)
+    l = torch.nn.functional.mse_loss(r, torch.zeros_like(r))
+    l.backward()
+    assert abs(float(l.detach()) - loss) <= 1e-5 * abs(loss)
+    g_ref = torch.cat([p.grad.reshape(-1) for lin in ref.model.conv_block.linears for p in (lin.weight, lin.bias)])
+    g_our = grads[:g_ref.numel()]
+    assert float((g_our - g_ref).norm() / g_ref.norm()) <= 1e-4

@@ -16,6 +16,7 @@ def eval_expr(e, env, memo=None):
     if k == 'const': r = np.full_like(env['x'][0], e.value)
     elif k == 'coord': r = env['x'][e.value]
     elif k == 'u': r = env['u'][e.value]
+    elif k == 'ch': r = env['ch'][e.value]
     elif k == 'var': r = np.full_like(env['x'][0], env['v'][e.value])
     elif k == 'powi': r = eval_expr(e.args[0], env, memo) ** e.value
     else:
@@ -39,15 +40,10 @@ def test_program_equals_expression_and_partials(name):
     coords = np.stack([rng.uniform(lo, hi, n) for lo, hi in cfg['ranges']])
     C = tr.channels
     ujet = rng.normal(size=(C, n))
-    chan = {(): 0}
-    for d, col in enumerate(tr.dirs):
-        chan[(col,)] = 1 + d
-        if d < tr.ns:
-            chan[(col, col)] = 1 + tr.nf + d
     vvals = {nm: 0.7 + i for i, nm in enumerate(tr.var_names)}
 
     def env_of(uj):
-        return {'x': coords, 'u': {mi: uj[c] for mi, c in chan.items()}, 'v': vvals}
+        return {'x': coords, 'ch': uj, 'v': vvals}
     outs = T.run_program(tr.eq_prog, ujet, coords, [vvals[nm] for nm in tr.var_names])
     r0 = eval_expr(tr.residual, env_of(ujet))
     np.testing.assert_allclose(outs[0], r0, rtol=1e-12, atol=1e-12)
@@ -79,7 +75,7 @@ def test_ic_program_is_the_jet_of_ic():
     ic = 10 * x * y * (1 - x) * (1 - y)
     np.testing.assert_allclose(outs[0], ic, rtol=1e-12)
     # dirs = [x, y, t] with second order on x, y
-    assert tr.dirs == [0, 1, 2] and tr.ns == 2
+    assert tr.dirs == [0, 1, 2] and tr.ns == 2 and tr.dir_vecs[2] == [0.0, 0.0, 1.0]
     np.testing.assert_allclose(outs[1], 10 * y * (1 - y) * (1 - 2 * x), rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(outs[2], 10 * x * (1 - x) * (1 - 2 * y), rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(outs[3], 0 * x, atol=1e-12)
@@ -91,8 +87,8 @@ def test_not_lowerable_cases():
     D = T.sym_D
     with pytest.raises(T.NotLowerable):            # third order
         T.trace(lambda f, x: D(D(D(f, x), x), x), 1, None)
-    with pytest.raises(T.NotLowerable):            # mixed second derivative
-        T.trace(lambda f, x, y: D(D(f, x), y), 2, None)
+    with pytest.raises(T.NotLowerable):            # more than 4 directions (3 axes + 2 diagonals)
+        T.trace(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z), 3, None)
     with pytest.raises(T.NotLowerable):            # data-dependent branch
         T.trace(lambda f, x: f if x > 0 else -f, 1, None)
     with pytest.raises(T.NotLowerable):            # unsupported torch function
@@ -136,3 +132,16 @@ def test_derivative_with_respect_to_parameter_column_is_a_direction():
     D = T.sym_D
     tr = T.trace(lambda f, x, e: D(f, x) + D(f, e) * e, 2, None)
     assert tr.dirs == [0, 1] and tr.ns == 0
+
+
+def test_mixed_derivative_is_polarised_onto_a_diagonal_direction():
+    D = T.sym_D
+    tr = T.trace(lambda f, x, y: D(D(f, x), y) - D(D(f, y), x) + D(D(f, x), y), 2, None)
+    assert tr.dirs == [0, 1, -1] and tr.dir_vecs[2] == [1.0, 1.0] and tr.ns == 3 and tr.nf == 3
+    # residual == u_xy = (U_vv - U_xx - U_yy) / 2 with channels [u, x, y, v, xx, yy, vv]
+    n = 8
+    rng = np.random.RandomState(0)
+    ujet = rng.normal(size=(tr.channels, n))
+    outs = T.run_program(tr.eq_prog, ujet, np.zeros((2, n)), [])
+    np.testing.assert_allclose(outs[0], 0.5 * (ujet[6] - ujet[4] - ujet[5]), rtol=1e-12)
+    np.testing.assert_allclose(outs[1 + 6], 0.5 * np.ones(n)); np.testing.assert_allclose(outs[1 + 4], -0.5 * np.ones(n))
