@@ -171,7 +171,9 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     os.environ.setdefault('PYDENS_B200_PROGRESS', '0')
-    os.environ['NCCL_DEBUG'] = os.environ.get('PYDENS_B200_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+    if 'PYDENS_B200_NCCL_DEBUG' not in os.environ:                 # keep stdout to the one JSON line
+        os.environ.pop('NCCL_DEBUG', None)
+        os.environ['NCCL_DEBUG_FILE'] = '/dev/null'
 
     if args.impl == 'reference':
         if rank != 0:
@@ -230,8 +232,8 @@ def main():
     ring = torch.zeros(K + W + 8, device=dev)
 
     def step(i, pts):
-        eng._step(pts, None, local_n, inv_n, offset)
-        if world > 1:
+        eng._step(pts, None, local_n, inv_n, offset, allreduce=world > 1)
+        if world > 1 and eng.comm is None:
             dist.all_reduce(eng.out)
         opt.step()
         _native.check(eng.lib.pinn_record_loss(eng.plan, C.c_void_p(eng.out.data_ptr()), C.c_void_p(ring.data_ptr()),
@@ -374,6 +376,8 @@ def main():
                               'in-kernel Philox sampling variant reported as value_sampled'
                               % (pool_n, pool.numel() * 4 / 1e6, ' > L2' if pool.numel() * 4 > 126e6 else ''),
                        cuda_graph=graphed, final_loss=last_loss,
+                       allreduce=('in-kernel over NVLink peer memory (pinn_step_allreduce)' if eng.comm is not None
+                                  else ('NCCL' if world > 1 else 'none')),
                        kernel='step_kernel<NF=%d,NS=%d> %d threads/CTA x %d CTAs, %d B smem, %d regs, activations in %s'
                               % (info.nf, info.ns, info.threads_per_cta, min(info.sm_count, (local_n + info.threads_per_cta - 1) // info.threads_per_cta),
                                  info.smem_bytes, info.regs_per_thread, 'smem' if info.activations_in_smem else 'gmem')),

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   6
+#define PINN_ABI_VERSION   7
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -227,6 +227,36 @@ int pinn_step(const PinnPlan* plan,
               float* residual_out,
               void* workspace, size_t workspace_bytes,
               void* stream);
+
+/*
+ * Data-parallel runs: the all-reduce of [grads | loss] fused into the tail of the step kernel, over
+ * NVLink peer memory — no NCCL call, no extra launch.  (The reference has no multi-device path; this
+ * is the B200-native form of "one all-reduce of the tiny gradient buffer per step".)
+ *
+ *   pinn_comm_create   allocates this rank's exchange buffer (cudaMalloc inside the library so that it
+ *                      can be shared through CUDA IPC) and returns its 64-byte IPC handle;
+ *   pinn_comm_connect  maps the buffers of all ranks of the SAME node from their handles (gathered by
+ *                      the caller, e.g. with torch.distributed.all_gather_object), rank-ordered;
+ *   pinn_step_allreduce  == pinn_step, except that `grads_and_loss` receives the SUM over all ranks:
+ *                      the last CTA stores the rank's vector into its slot of every rank's buffer
+ *                      (peer stores), publishes an arrival flag (release, system scope), waits for the
+ *                      flags of all ranks and sums the slots in rank order, so every rank holds
+ *                      bit-identical results.  All ranks must issue the same sequence of calls.  If a
+ *                      peer does not arrive within ~4 s the outputs are set to NaN instead of hanging.
+ */
+#define PINN_COMM_HANDLE_BYTES 64
+#define PINN_COMM_MAX_RANKS     8
+typedef struct PinnComm PinnComm;
+int pinn_comm_create(const PinnPlan* plan, int rank, int world, PinnComm** comm,
+                     unsigned char handle_out[PINN_COMM_HANDLE_BYTES]);
+int pinn_comm_connect(PinnComm* comm, const unsigned char* handles /* world x 64 bytes, rank order */);
+int pinn_comm_destroy(PinnComm* comm);
+int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm,
+                        const float* params, const float* points, const PinnColumn* cols,
+                        uint64_t seed, const uint64_t* step_counter, uint64_t step_value,
+                        uint64_t point_offset, int64_t n_points, float inv_global_n,
+                        float* grads_and_loss, float* residual_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Forward only: u = ansatz(net(x)) for explicit points — the work of Solver.predict
  * (model_torch.py:466-487) and of the `_forward` closure handed to constraints (:451-454).

@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3}
@@ -68,7 +68,8 @@ class PinnPlanInfo(C.Structure):
 
 EXPORTS = ('pinn_last_error', 'pinn_abi_version', 'pinn_plan_create', 'pinn_plan_destroy',
            'pinn_workspace_bytes', 'pinn_out_floats', 'pinn_step', 'pinn_forward', 'pinn_sample',
-           'pinn_record_loss', 'pinn_plan_info')
+           'pinn_record_loss', 'pinn_plan_info', 'pinn_comm_create', 'pinn_comm_connect', 'pinn_comm_destroy',
+           'pinn_step_allreduce')
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpinn_b200.so')
 _lib = None
@@ -103,6 +104,10 @@ def load():
     lib.pinn_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PinnColumn), C.c_uint64, C.c_void_p,
                               C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pinn_step_allreduce.argtypes = [C.c_void_p] + lib.pinn_step.argtypes
+    lib.pinn_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.pinn_comm_connect.argtypes = [C.c_void_p, C.c_char_p]
+    lib.pinn_comm_destroy.argtypes = [C.c_void_p]
     lib.pinn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p]
     lib.pinn_sample.argtypes = [C.c_void_p, C.POINTER(PinnColumn), C.c_uint64, C.c_void_p, C.c_uint64,

@@ -271,10 +271,72 @@ static int resolve_cols(const PinnPlan* p, const PinnColumn* cols, PinnColumn* o
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
-extern "C" int pinn_step(const PinnPlan* cp, const float* params, const float* points, const PinnColumn* cols,
-                         uint64_t seed, const uint64_t* step_counter, uint64_t step_value, uint64_t point_offset,
-                         int64_t n_points, float inv_global_n, float* grads_and_loss, float* residual_out,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+struct PinnComm {
+    int rank, world, device;
+    char* local;                              // this rank's exchange buffer (cudaMalloc)
+    char* peers[PINN_COMM_MAX_RANKS];         // every rank's buffer as mapped here (peers[rank] == local)
+    bool connected;
+    size_t bytes;
+};
+
+extern "C" int pinn_comm_create(const PinnPlan* p, int rank, int world, PinnComm** out,
+                                unsigned char handle_out[PINN_COMM_HANDLE_BYTES]) {
+    if (!p || !out || !handle_out) return fail(PINN_E_INVALID, "null argument");
+    if (world < 2 || world > PINN_COMM_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(PINN_E_INVALID, "rank %d / world %d (2..%d ranks of one node)", rank, world, PINN_COMM_MAX_RANKS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == PINN_COMM_HANDLE_BYTES, "IPC handle size");
+    PinnComm* c = new (std::nothrow) PinnComm();
+    if (!c) return fail(PINN_E_INVALID, "out of memory");
+    c->rank = rank; c->world = world; c->device = p->device; c->connected = false; c->local = nullptr;
+    for (int r = 0; r < PINN_COMM_MAX_RANKS; ++r) c->peers[r] = nullptr;
+    c->bytes = comm_bytes(p->h.n_params + 4, world);
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->local, c->bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, c->bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+    if (e != cudaSuccess) {
+        if (c->local) cudaFree(c->local);
+        delete c;
+        return fail(PINN_E_CUDA, "pinn_comm_create: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, PINN_COMM_HANDLE_BYTES);
+    c->peers[rank] = c->local;
+    *out = c;
+    return PINN_OK;
+}
+
+extern "C" int pinn_comm_connect(PinnComm* c, const unsigned char* handles) {
+    if (!c || !handles) return fail(PINN_E_INVALID, "null argument");
+    if (c->connected) return PINN_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * PINN_COMM_HANDLE_BYTES, PINN_COMM_HANDLE_BYTES);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(PINN_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        c->peers[r] = static_cast<char*>(ptr);
+    }
+    c->connected = true;
+    return PINN_OK;
+}
+
+extern "C" int pinn_comm_destroy(PinnComm* c) {
+    if (!c) return PINN_OK;
+    cudaSetDevice(c->device);
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return PINN_OK;
+}
+
+static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* params, const float* points,
+                     const PinnColumn* cols, uint64_t seed, const uint64_t* step_counter, uint64_t step_value,
+                     uint64_t point_offset, int64_t n_points, float inv_global_n, float* grads_and_loss,
+                     float* residual_out, void* workspace, size_t workspace_bytes, void* stream) {
     PinnPlan* p = const_cast<PinnPlan*>(cp);
     if (!p || !params || !grads_and_loss || !workspace) return fail(PINN_E_INVALID, "null argument");
     if (n_points <= 0) return fail(PINN_E_INVALID, "n_points must be positive");
@@ -283,6 +345,8 @@ extern "C" int pinn_step(const PinnPlan* cp, const float* params, const float* p
     if (points && (((uintptr_t)points) & 3u)) return fail(PINN_E_ALIGN, "points must be 4-byte aligned");
     if (workspace_bytes < pinn_workspace_bytes(p, n_points))
         return fail(PINN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, pinn_workspace_bytes(p, n_points));
+    if (comm && (!comm->connected || comm->bytes != comm_bytes(p->h.n_params + 4, comm->world)))
+        return fail(PINN_E_INVALID, "communicator is not connected or belongs to another plan");
     cudaStream_t st = (cudaStream_t)stream;
     DevPlan plan = p->h;
     if (!points) { int rc = resolve_cols(p, cols, plan.cols); if (rc) return rc; }
@@ -294,11 +358,32 @@ extern "C" int pinn_step(const PinnPlan* cp, const float* params, const float* p
     a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_partials_off());
     a.spill = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_spill_off(p));
     a.n_wacc = p->n_wacc; a.rows_total = p->h.rows_total;
+    a.comm_rank = comm ? comm->rank : 0;
+    a.comm_world = comm ? comm->world : 0;
+    for (int r = 0; r < PINN_COMM_MAX_RANKS; ++r) a.comm_peers[r] = comm ? comm->peers[r] : nullptr;
     const int grid = grid_for(p, n_points, p->threads);
     StepKernelFn fn = p->gmem ? p->var->gmem_fn : p->var->smem_fn;
     fn<<<grid, p->threads, p->smem_bytes, st>>>(plan, a);
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;
+}
+
+extern "C" int pinn_step(const PinnPlan* plan, const float* params, const float* points, const PinnColumn* cols,
+                         uint64_t seed, const uint64_t* step_counter, uint64_t step_value, uint64_t point_offset,
+                         int64_t n_points, float inv_global_n, float* grads_and_loss, float* residual_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    return step_impl(plan, nullptr, params, points, cols, seed, step_counter, step_value, point_offset, n_points,
+                     inv_global_n, grads_and_loss, residual_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm, const float* params,
+                                   const float* points, const PinnColumn* cols, uint64_t seed,
+                                   const uint64_t* step_counter, uint64_t step_value, uint64_t point_offset,
+                                   int64_t n_points, float inv_global_n, float* grads_and_loss, float* residual_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!comm) return fail(PINN_E_INVALID, "null communicator");
+    return step_impl(plan, comm, params, points, cols, seed, step_counter, step_value, point_offset, n_points,
+                     inv_global_n, grads_and_loss, residual_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int pinn_forward(const PinnPlan* p, const float* params, const float* points, int64_t n_points,

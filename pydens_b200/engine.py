@@ -92,15 +92,44 @@ class FusedEngine:
         self.steps_done = 0
         self.seed = solver.seed
 
+        self.comm = None
         dist = _dist()
         if dist is not None:
             seed_t = torch.tensor([self.seed], dtype=torch.int64, device=self.device)
             dist.broadcast(seed_t, 0)
             self.seed = int(seed_t.item())
             dist.broadcast(self.flat, 0)
+            self._connect_peers(dist)
+
+    def _connect_peers(self, dist):
+        """ Set up the in-kernel all-reduce over NVLink peer memory (pinn_step_allreduce): every rank
+        allocates an exchange buffer inside the library, the CUDA-IPC handles are gathered and mapped.
+        Any failure (no peer access, more than 8 ranks, several nodes) leaves NCCL in charge. """
+        if os.environ.get('PYDENS_B200_FUSED_ALLREDUCE', '1') == '0':
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ok, comm = 1, C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if world > 8 or self.lib.pinn_comm_create(self.plan, rank, world, C.byref(comm), handle) != 0:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if ok else None)
+        if ok and all(h is not None for h in handles):
+            ok = int(self.lib.pinn_comm_connect(comm, b''.join(handles)) == 0)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # all ranks or none
+        if int(flag.item()) == 1:
+            self.comm = comm
+        elif comm:
+            self.lib.pinn_comm_destroy(comm)
 
     def __del__(self):
         try:
+            if getattr(self, 'comm', None):
+                self.lib.pinn_comm_destroy(self.comm)
+                self.comm = None
             if getattr(self, 'plan', None):
                 self.lib.pinn_plan_destroy(self.plan)
                 self.plan = None
@@ -118,16 +147,20 @@ class FusedEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _step(self, points, cols, n_points, inv_n, point_offset, residual=None, use_counter=True, step_value=0):
-        _native.check(self.lib.pinn_step(
-            self.plan, C.c_void_p(self.flat.data_ptr()),
-            C.c_void_p(points.data_ptr()) if points is not None else None,
-            cols, C.c_uint64(self.seed),
-            C.c_void_p(self.step_counter.data_ptr()) if use_counter else None, C.c_uint64(step_value),
-            C.c_uint64(point_offset), C.c_int64(n_points), C.c_float(inv_n),
-            C.c_void_p(self.out.data_ptr()),
-            C.c_void_p(residual.data_ptr()) if residual is not None else None,
-            C.c_void_p(self.workspace.data_ptr()), C.c_size_t(self.workspace.numel()), self._stream()))
+    def _step(self, points, cols, n_points, inv_n, point_offset, residual=None, use_counter=True, step_value=0,
+              allreduce=False):
+        args = (C.c_void_p(self.flat.data_ptr()),
+                C.c_void_p(points.data_ptr()) if points is not None else None,
+                cols, C.c_uint64(self.seed),
+                C.c_void_p(self.step_counter.data_ptr()) if use_counter else None, C.c_uint64(step_value),
+                C.c_uint64(point_offset), C.c_int64(n_points), C.c_float(inv_n),
+                C.c_void_p(self.out.data_ptr()),
+                C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                C.c_void_p(self.workspace.data_ptr()), C.c_size_t(self.workspace.numel()), self._stream())
+        if allreduce and self.comm is not None:
+            _native.check(self.lib.pinn_step_allreduce(self.plan, self.comm, *args))
+        else:
+            _native.check(self.lib.pinn_step(self.plan, *args))
 
     def loss_and_grads(self, points):
         pts = torch.as_tensor(points, dtype=torch.float32).to(self.device).contiguous()
@@ -203,9 +236,9 @@ class FusedEngine:
             zero_host = torch.zeros(max(niters, 1), dtype=torch.float32).pin_memory()
 
         def one_step(i, points=None):
-            self._step(points, cols, local_n, inv_n, point_offset)
-            if dist is not None:
-                dist.all_reduce(self.out)
+            self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
+            if dist is not None and self.comm is None:
+                dist.all_reduce(self.out)              # no peer-memory path: NCCL sums [grads | loss]
             if nums:
                 xs = solver._sample_host(sampler if host_sampler is not None else None, batch_size) \
                     if points is None else [points[:, k:k + 1] for k in range(total)]

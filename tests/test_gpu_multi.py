@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, out):
-    env = dict(os.environ, PYDENS_B200_PROGRESS='0')
+def _run(world, out, fused='1'):
+    env = dict(os.environ, PYDENS_B200_PROGRESS='0', PYDENS_B200_FUSED_ALLREDUCE=fused)
     script = os.path.join(ROOT, 'tools', 'check_dp.py')
     if world == 1:
         cmd = [sys.executable, script, out]
@@ -28,8 +28,11 @@ def _run(world, out):
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_two_gpu_fit_matches_single_gpu(tmp_path):
     one = _run(1, str(tmp_path / 'w1.json'))
-    two = _run(2, str(tmp_path / 'w2.json'))
-    a, b = np.asarray(one['losses']), np.asarray(two['losses'])
-    assert a.shape == b.shape == (30,)
-    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-4
-    assert abs(one['params_norm'] - two['params_norm']) <= 1e-4 * one['params_norm']
+    a = np.asarray(one['losses'])
+    for fused, mode in (('1', 'peer'), ('0', 'nccl')):     # in-kernel NVLink all-reduce, then plain NCCL
+        two = _run(2, str(tmp_path / ('w2_%s.json' % mode)), fused)
+        assert two['allreduce'] == mode
+        b = np.asarray(two['losses'])
+        assert a.shape == b.shape == (30,)
+        assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-4
+        assert abs(one['params_norm'] - two['params_norm']) <= 1e-4 * one['params_norm']

@@ -42,7 +42,9 @@ def main():
         dist.broadcast(ref, 0)
         assert torch.equal(ref, flat), 'replicas diverged'
     if (not dist.is_initialized()) or dist.get_rank() == 0:
-        json.dump({'world': world, 'losses': losses, 'params_norm': float(flat.norm())}, open(out, 'w'))
+        eng = solver._get_engine()
+        json.dump({'world': world, 'losses': losses, 'params_norm': float(flat.norm()),
+                   'allreduce': 'peer' if eng.comm is not None else ('nccl' if world > 1 else 'none')}, open(out, 'w'))
     if world > 1:
         dist.destroy_process_group()
 
