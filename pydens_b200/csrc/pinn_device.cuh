@@ -67,6 +67,7 @@ struct alignas(16) DevPlan {
     int eq_out[1 + 1 + 2 * PINN_MAX_DIRS + PINN_MAX_VARS];
     int ic_out[(1 + 2 * PINN_MAX_DIRS) * (1 + PINN_MAX_VARS)];
     int ic_has_vars;
+    int general;                // 1: residual layouts / non-axis directions / variables in the initial condition present
     PinnColumn cols[PINN_MAX_DIMS];     // sampler columns of the current call
     DevLayer layer[PINN_MAX_LAYERS];
     PinnInstr eq[PINN_MAX_PROG];
@@ -335,10 +336,11 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
 // Where a consumer reads the (activated) output of layer p: a residual layer keeps the sum
 // act(z_p) + skip in its post buffer, which reads back like the output of an identity activation;
 // any other layer is rebuilt from its stored jet with its own activation.
+template <bool GEN = true>
 PINN_HD const float* layer_output(const DevPlan& P, int p, const float* __restrict__ units, int C, int RS,
                                   int& act_id) {
     const DevLayer& Lp = P.layer[p];
-    if (Lp.post_base >= 0) { act_id = PINN_ACT_NONE; return units + (size_t)Lp.post_base * C * RS; }
+    if (GEN && Lp.post_base >= 0) { act_id = PINN_ACT_NONE; return units + (size_t)Lp.post_base * C * RS; }
     act_id = Lp.act;
     return units + (size_t)Lp.unit_base * C * RS;
 }
@@ -455,7 +457,7 @@ struct AnsatzState {
     float v, vd[NF > 0 ? NF : 1], vdd[NS > 0 ? NS : 1];       // BC-transformed value jet
 };
 
-template <int NF, int NS>
+template <int NF, int NS, bool GEN = true>
 PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, int RS, float log_scale,
                             const float (&N)[1 + NF + NS], const float* __restrict__ icj /* C or null */,
                             AnsatzState<NF, NS>& st, float (&u)[1 + NF + NS]) {
@@ -473,7 +475,7 @@ PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, 
 #pragma unroll
         for (int d = 0; d < NF; ++d) {
             const int k = P.dir_col[d];
-            if (k >= 0) {                                 // unit vector of column k
+            if (!GEN || k >= 0) {                         // unit vector of column k
                 if (k < P.nsp) {
                     float others = 1.0f;
                     for (int i = 0; i < P.nsp; ++i) {
@@ -858,7 +860,7 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
 template <int NF, int NS>
 struct PointPartials { float loss, sbar, vbar[PINN_MAX_VARS]; };
 
-template <int NF, int NS, int JF>
+template <int NF, int NS, int JF, bool GEN = true>
 PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weights */,
                          const float* __restrict__ pvals /* flat params (for log_scale, V) */,
                          float* __restrict__ st, int RS, bool valid, float inv_n,
@@ -874,16 +876,16 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
     for (int l = 0; l + 1 < Ln; ++l) {
         const DevLayer& L = P.layer[l];
         int in_act = PINN_ACT_NONE;
-        const float* in_rows = (l == 0) ? coords : layer_output(P, l - 1, units, C, RS, in_act);
+        const float* in_rows = (l == 0) ? coords : layer_output<GEN>(P, l - 1, units, C, RS, in_act);
         fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, &P.dir_vec[0][0],
                               units + (size_t)L.unit_base * C * RS, RS);
-        if (L.skip_src >= 0) skip_sum_pass<NF, NS>(P, l, units, RS);
+        if (GEN && L.skip_src >= 0) skip_sum_pass<NF, NS>(P, l, units, RS);
     }
     float N[C];
     {
         const DevLayer& L = P.layer[Ln - 1];
         int in_act = PINN_ACT_NONE;
-        const float* in_rows = (Ln == 1) ? coords : layer_output(P, Ln - 2, units, C, RS, in_act);
+        const float* in_rows = (Ln == 1) ? coords : layer_output<GEN>(P, Ln - 2, units, C, RS, in_act);
         fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, &P.dir_vec[0][0], RS, N);
     }
 
@@ -899,7 +901,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
     float log_scale = pvals[P.log_scale_off];
     AnsatzState<NF, NS> as;
     float u[C];
-    ansatz_forward<NF, NS>(P, coords, RS, log_scale, N, icj, as, u);
+    ansatz_forward<NF, NS, GEN>(P, coords, RS, log_scale, N, icj, as, u);
 #pragma unroll
     for (int c = 0; c < C; ++c) scr[(size_t)c * RS] = u[c];
     eval_prog(P.eq, P.n_eq, scr, RS, coords, pvals, P.var_off);
@@ -912,7 +914,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
 #pragma unroll
     for (int i = 0; i < PINN_MAX_VARS; ++i)
         if (i < P.n_vars) part.vbar[i] = fmaf(rb, scr[(size_t)P.eq_out[1 + C + i] * RS], part.vbar[i]);
-    if (P.ic_has_vars) {                       // u_c = S v_c + ic_c: variables of the initial condition
+    if (GEN && P.ic_has_vars) {                // u_c = S v_c + ic_c: variables of the initial condition
 #pragma unroll
         for (int i = 0; i < PINN_MAX_VARS; ++i) {
             if (i < P.n_vars) {
@@ -940,10 +942,10 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const DevLayer& B = P.layer[l - 1];                 // the layer below
         float* in_rows = units + (size_t)B.unit_base * C * RS;
         int load_act;
-        const float* load_rows = layer_output(P, l - 1, units, C, RS, load_act);
+        const float* load_rows = layer_output<GEN>(P, l - 1, units, C, RS, load_act);
         const float* adj_in = B.adj_from >= 0 ? units + (size_t)P.layer[B.adj_from].post_base * C * RS : nullptr;
         float* adj_out = B.skip_src >= 0 ? units + (size_t)B.post_base * C * RS : nullptr;
-        if (B.post_base >= 0 || B.adj_from >= 0) {          // residual wiring around the layer below (rare path)
+        if (GEN && (B.post_base >= 0 || B.adj_from >= 0)) { // residual wiring around the layer below (rare path)
             if (L.n_out == 1) bwd_layer<NF, NS, 1, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
             else              bwd_layer<NF, NS, 4, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
         } else {

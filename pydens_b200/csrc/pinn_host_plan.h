@@ -129,6 +129,9 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
         L.skip_src = src; L.post_base = units; units += L.n_out;
         h.layer[src].adj_from = l;
     }
+    h.general = h.ic_has_vars;
+    for (int l = 0; l < Ln; ++l) if (h.layer[l].skip_src >= 0) h.general = 1;
+    for (int d = 0; d < s->nf; ++d) if (s->dir_col[d] < 0) h.general = 1;
     h.weights_floats = round_up_i(sw, 4);
     h.n_units = units;
     h.row_units = total;

@@ -100,23 +100,31 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(PINN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
-static const Variant* find_variant(int nf, int ns) {
-    if (ns < 0 || ns > nf) return nullptr;
+// The function table of one (nf, ns): its two halves live in sibling translation units.
+static bool find_variant(int nf, int ns, Variant& out) {
+    if (ns < 0 || ns > nf) return false;
+    const Variant *a = nullptr, *b = nullptr;
     switch (nf) {
-        case 0: return pinn_variants_nf0(ns);
-        case 1: return pinn_variants_nf1(ns);
-        case 2: return pinn_variants_nf2(ns);
-        case 3: return pinn_variants_nf3(ns);
-        case 4: return pinn_variants_nf4(ns);
-        default: return nullptr;
+        case 0: a = pinn_variants_nf0(ns); b = pinn_variants_gen_nf0(ns); break;
+        case 1: a = pinn_variants_nf1(ns); b = pinn_variants_gen_nf1(ns); break;
+        case 2: a = pinn_variants_nf2(ns); b = pinn_variants_gen_nf2(ns); break;
+        case 3: a = pinn_variants_nf3(ns); b = pinn_variants_gen_nf3(ns); break;
+        case 4: a = pinn_variants_nf4(ns); b = pinn_variants_gen_nf4(ns); break;
+        default: return false;
     }
+    if (!a || !b) return false;
+    out = *a;
+    out.smem_gen_fn = b->smem_gen_fn; out.gmem_gen_fn = b->gmem_gen_fn;
+    return true;
 }
 
 struct PinnPlan {
     PinnSpec spec;
     DevPlan h;
     int device;
+    Variant var_store;
     const Variant* var;
+    StepKernelFn fn_smem, fn_gmem;           // the pair matching this plan (plain or general)
     int sm_count;
     int smem_optin;
     // step kernel launch config
@@ -141,8 +149,10 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         int rc = build_dev_plan(s, p->h, p->fwd_rows, p->fwd_row_scr, msg, sizeof(msg));
         if (rc) { delete p; return fail(rc, "%s", msg); }
     }
-    var = find_variant(s->nf, s->ns);
-    if (!var) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns); }
+    if (!find_variant(s->nf, s->ns, p->var_store)) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns); }
+    var = &p->var_store;
+    p->fn_smem = p->h.general ? var->smem_gen_fn : var->smem_fn;
+    p->fn_gmem = p->h.general ? var->gmem_gen_fn : var->gmem_fn;
     p->spec = *s;
     p->device = device;
     p->var = var;
@@ -161,7 +171,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
 
     const int n_out_floats = s->n_params + 4;
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void*)var->smem_fn);
+    e = cudaFuncGetAttributes(&fa, (const void*)p->fn_smem);
     if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); }
     p->regs = fa.numRegs;
     int max_warps_regs = (65536 / (fa.numRegs * 32));
@@ -191,7 +201,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         p->smem_bytes = SL.total_f * 4;
     } else {
         // activations spill to a global workspace; accumulators: per warp if they fit, else shared
-        e = cudaFuncGetAttributes(&fa, (const void*)var->gmem_fn);
+        e = cudaFuncGetAttributes(&fa, (const void*)p->fn_gmem);
         if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); }
         p->regs = fa.numRegs;
         int nw = var->maxt / 32;
@@ -202,7 +212,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         if (SL.total_f * 4 > budget) { delete p; return fail(PINN_E_UNSUPPORTED, "network too large: %d B of weights do not fit shared memory", SL.total_f * 4); }
         p->gmem = true; p->threads = nw * 32; p->n_wacc = nwacc; p->smem_bytes = SL.total_f * 4;
     }
-    e = cudaFuncSetAttribute((const void*)(p->gmem ? var->gmem_fn : var->smem_fn),
+    e = cudaFuncSetAttribute((const void*)(p->gmem ? p->fn_gmem : p->fn_smem),
                              cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
     if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", p->smem_bytes, cudaGetErrorString(e)); }
 
@@ -362,7 +372,7 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
     a.comm_world = comm ? comm->world : 0;
     for (int r = 0; r < PINN_COMM_MAX_RANKS; ++r) a.comm_peers[r] = comm ? comm->peers[r] : nullptr;
     const int grid = grid_for(p, n_points, p->threads);
-    StepKernelFn fn = p->gmem ? p->var->gmem_fn : p->var->smem_fn;
+    StepKernelFn fn = p->gmem ? p->fn_gmem : p->fn_smem;
     fn<<<grid, p->threads, p->smem_bytes, st>>>(plan, a);
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;

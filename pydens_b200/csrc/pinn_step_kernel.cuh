@@ -156,7 +156,7 @@ __device__ __forceinline__ void stage_weights(float* smem, const SmemLayout& SL,
 // ---------------------------------------------------------------------------------------------------
 // The fit-step kernel.
 // ---------------------------------------------------------------------------------------------------
-template <int NF, int NS, bool GMEM, int MAXT, int JF>
+template <int NF, int NS, bool GMEM, int MAXT, int JF, bool GEN>
 __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ DevPlan P, const StepArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
                                    (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             for (int k = 0; k < P.total; ++k) st[k * RS] = sample_column(P.cols[k], k, gidx, step, a.seed, b0, b1);
         }
-        float r = point_step<NF, NS, JF>(P, sw, a.params, st, RS, valid, a.inv_n, sink, part);
+        float r = point_step<NF, NS, JF, GEN>(P, sw, a.params, st, RS, valid, a.inv_n, sink, part);
         if (a.residual && valid) a.residual[pl] = r;
     }
 
@@ -319,7 +319,8 @@ typedef void (*StepKernelFn)(const DevPlan, const StepArgs);
 
 struct Variant {
     int nf, ns;
-    StepKernelFn smem_fn, gmem_fn;
+    StepKernelFn smem_fn, gmem_fn;           // plain problems (no residual wiring / oblique directions / IC variables)
+    StepKernelFn smem_gen_fn, gmem_gen_fn;   // everything
     int maxt;
 };
 
@@ -330,13 +331,21 @@ struct VariantCfg {
     static constexpr int JF = 16;
 };
 
-template <int NF, int NS>
+// `gen` selects which half of the function table this translation unit instantiates (the other half is
+// filled by its sibling unit), so that the two halves compile in parallel.
+template <int NF, int NS, bool GEN>
 static Variant make_variant() {
     using Cfg = VariantCfg<NF, NS>;
     Variant v;
     v.nf = NF; v.ns = NS;
-    v.smem_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF>;
-    v.gmem_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF>;
+    v.smem_fn = v.gmem_fn = v.smem_gen_fn = v.gmem_gen_fn = nullptr;
+    if (GEN) {
+        v.smem_gen_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF, GEN>;
+        v.gmem_gen_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF, GEN>;
+    } else {
+        v.smem_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF, GEN>;
+        v.gmem_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF, GEN>;
+    }
     v.maxt = Cfg::MAXT;
     return v;
 }
@@ -349,3 +358,8 @@ const pinn::Variant* pinn_variants_nf1(int ns);
 const pinn::Variant* pinn_variants_nf2(int ns);
 const pinn::Variant* pinn_variants_nf3(int ns);
 const pinn::Variant* pinn_variants_nf4(int ns);
+const pinn::Variant* pinn_variants_gen_nf0(int ns);
+const pinn::Variant* pinn_variants_gen_nf1(int ns);
+const pinn::Variant* pinn_variants_gen_nf2(int ns);
+const pinn::Variant* pinn_variants_gen_nf3(int ns);
+const pinn::Variant* pinn_variants_gen_nf4(int ns);

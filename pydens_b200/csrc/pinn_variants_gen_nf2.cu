@@ -1,0 +1,4 @@
+// step_kernel instantiations for NF = 2 first-order directions, general problems (see pinn_variants.inc)
+#define PINN_VARIANT_NF 2
+#define PINN_VARIANT_GEN 1
+#include "pinn_variants.inc"

@@ -1,3 +1,4 @@
-// step_kernel instantiations for NF = 1 first-order directions (see pinn_variants.inc)
+// step_kernel instantiations for NF = 1 first-order directions, plain problems (see pinn_variants.inc)
 #define PINN_VARIANT_NF 1
+#define PINN_VARIANT_GEN 0
 #include "pinn_variants.inc"

@@ -23,7 +23,9 @@ static void run_step(const DevPlan& P, const float* sw, const float* params, con
     for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
     for (long long p = 0; p < n; ++p) {
         for (int k = 0; k < P.total; ++k) st[k] = points[p * P.total + k];
-        float r = point_step<NF, NS, 16>(P, sw, params, st.data(), 1, true, inv_n, sink, part);
+        // both instantiations the CUDA build uses: the plain one when the plan allows it, else the general one
+        float r = P.general ? point_step<NF, NS, 16, true>(P, sw, params, st.data(), 1, true, inv_n, sink, part)
+                            : point_step<NF, NS, 16, false>(P, sw, params, st.data(), 1, true, inv_n, sink, part);
         if (residual) residual[p] = r;
     }
     out[P.n_params] += part.loss;
