@@ -51,3 +51,19 @@ def test_plan_create_rejects_bad_spec_without_gpu():
     rc = lib.pinn_plan_create(C.byref(spec), 0, C.byref(plan))
     assert rc == _native.E_INVALID
     assert b'abi_version' in lib.pinn_last_error()
+
+
+def test_library_is_sm100a_and_stages_weights_with_tma():
+    """ The shipped .so holds sm_100a SASS whose step kernel stages the parameters with a TMA bulk copy
+    (cp.async.bulk -> SASS UBLKCP) tracked by an mbarrier (SYNCS.*), and reduces with SHFL butterflies. """
+    import shutil
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    fn = '_ZN4pinn11step_kernelILi2ELi2ELb0ELi256ELi16ELb0EEEvNS_7DevPlanENS_8StepArgsE'
+    out = subprocess.run([cuobjdump, '-sass', '-fun', fn, _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out or 'SM100' in out.upper() or 'EF_CUDA_SM100' in out, out[:300]
+    assert 'UBLKCP' in out                                  # TMA bulk copy global -> shared
+    assert 'SYNCS' in out                                   # mbarrier expect_tx / try_wait
+    assert out.count('SHFL.BFLY') >= 31                     # transposing butterfly of the gradient reduction
+    assert 'LDS.128' in out                                 # broadcast 128-bit weight loads
