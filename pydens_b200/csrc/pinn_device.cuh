@@ -168,7 +168,8 @@ PINN_HD float tanh_acc(float x) {
     const float small = fmaf(p * x2, ax, ax);
 #if defined(__CUDA_ARCH__)
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));
+    // volatile: without it the compiler turns the select below into a branch around the MUFU ops
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));
     const float big = fmaf(-2.0f, __frcp_rn(e + 1.0f), 1.0f);
 #else
     const float e = exp2f(ax * 2.8853900817779268f);
@@ -684,6 +685,16 @@ PINN_HD void emit_entries(float (&v)[NV], AddFn&& add) {
 struct GradSink {
     float* wacc;        // accumulator in params layout (+ loss slot) for this warp / CTA
     bool atomic;        // true when several warps share one accumulator
+    int dump;           // index of a scratch slot of the accumulator that swallows masked-off entries
+    // add `val` at `idx` when `valid`; branch-free when the accumulator is private to the warp
+    PINN_HD void add_if(bool valid, int idx, float val) const {
+#if defined(__CUDA_ARCH__)
+        if (atomic) { if (valid) atomicAdd(wacc + idx, val); }
+        else { const int i = valid ? idx : dump; wacc[i] += val; }
+#else
+        if (valid) wacc[idx] += val;
+#endif
+    }
     PINN_HD void add(int idx, float val) const {
 #if defined(__CUDA_ARCH__)
         if (atomic) atomicAdd(wacc + idx, val); else wacc[idx] += val;
@@ -706,7 +717,8 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
                        const GradSink& sink,
                        const float* __restrict__ load_rows, int load_act_id,
                        const float* __restrict__ adj_in /* stashed skip adjoint to add, or null */,
-                       float* __restrict__ adj_out /* where to stash the adjoint of a residual layer, or null */) {
+                       float* __restrict__ adj_out /* where to stash the adjoint of a residual layer, or null */,
+                       float* __restrict__ dump_rows /* C rows that swallow the stores of masked-off units */) {
     constexpr int C = 1 + NF + NS;
     constexpr int JB = 8;
     const float* W = sw + L.w_s;
@@ -769,24 +781,23 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
             }
             emit_entries<JJ * JB>(v, [&](int e, float t) {
                 const int j = j0 + e / JB, m = m0 + e % JB;
-                if (j < L.n_out && m <= L.n_in)
-                    sink.add(m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
+                sink.add_if(j < L.n_out && m <= L.n_in, m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
             });
         }
         // adjoints of the layer below: through its activation, stored in place
 #pragma unroll
         for (int mm = 0; mm < JB; ++mm) {
             const bool ok = m0 + mm < L.n_in;
-            float* row = in_rows + (size_t)(ok ? m0 + mm : 0) * C * RS;
+            const float* row = in_rows + (size_t)(ok ? m0 + mm : 0) * C * RS;
             float pre[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
             ActD f = act_from_stored(below, pre[0]);
             float zb[C];
             act_adjoint<NF, NS>(f, pre, acc[mm], zb);
+            float* wrow = ok ? in_rows + (size_t)(m0 + mm) * C * RS : dump_rows;   // masked-off units: dump rows
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                if (ok) row[(size_t)c * RS] = zb[c];
+            for (int c = 0; c < C; ++c) wrow[(size_t)c * RS] = zb[c];
             if (SKIP && adj_out) {                        // residual layer: its skip source needs this adjoint too
                 float* srow = adj_out + (size_t)(ok ? m0 + mm : 0) * C * RS;
 #pragma unroll
@@ -810,7 +821,7 @@ PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, in
             v[i] = out_rows[(size_t)j * C * RS];
         }
         emit_entries<32>(v, [&](int e, float t) {
-            if (j0 + e < L.n_out) sink.add(L.b_off + j0 + e, t);
+            sink.add_if(j0 + e < L.n_out, L.b_off + j0 + e, t);
         });
     }
 }
@@ -846,8 +857,8 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
         }
         emit_entries<4 * PINN_MAX_DIMS>(v, [&](int e, float t) {
             const int j = j0 + e / PINN_MAX_DIMS, m = e % PINN_MAX_DIMS;
-            if (j < L.n_out && m <= L.n_in && m < PINN_MAX_DIMS)
-                sink.add(m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
+            sink.add_if(j < L.n_out && m <= L.n_in && m < PINN_MAX_DIMS,
+                        m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
         });
     }
     if (L.n_in >= PINN_MAX_DIMS) bias_grad<NF, NS>(L, out_rows, RS, sink);
@@ -946,11 +957,11 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const float* adj_in = B.adj_from >= 0 ? units + (size_t)P.layer[B.adj_from].post_base * C * RS : nullptr;
         float* adj_out = B.skip_src >= 0 ? units + (size_t)B.post_base * C * RS : nullptr;
         if (GEN && (B.post_base >= 0 || B.adj_from >= 0)) { // residual wiring around the layer below (rare path)
-            if (L.n_out == 1) bwd_layer<NF, NS, 1, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
-            else              bwd_layer<NF, NS, 4, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out);
+            if (L.n_out == 1) bwd_layer<NF, NS, 1, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out, scr);
+            else              bwd_layer<NF, NS, 4, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out, scr);
         } else {
-            if (L.n_out == 1) bwd_layer<NF, NS, 1, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr);
-            else              bwd_layer<NF, NS, 4, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr);
+            if (L.n_out == 1) bwd_layer<NF, NS, 1, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
+            else              bwd_layer<NF, NS, 4, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
         }
     }
     {

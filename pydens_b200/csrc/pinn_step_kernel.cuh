@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
     GradSink sink;
     sink.atomic = (a.n_wacc == 1 && nwarps > 1);
     sink.wacc = wacc_all + (a.n_wacc == 1 ? 0 : warp * n_out_floats);
+    sink.dump = P.n_params + 2;                    // spare float behind the loss slot
 
     const long long gw = (long long)blockIdx.x * nwarps + warp;         // global warp id
     const long long total_warps = (long long)gridDim.x * nwarps;

@@ -18,6 +18,7 @@ static void run_step(const DevPlan& P, const float* sw, const float* params, con
     GradSink sink;
     sink.wacc = out;
     sink.atomic = false;
+    sink.dump = P.n_params + 2;
     PointPartials<NF, NS> part;
     part.loss = 0.0f; part.sbar = 0.0f;
     for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
