@@ -222,7 +222,7 @@ def main():
         clocks.start()
 
     # ---------------- value: K graph-replayed steps over an HBM-resident pool of batches ----------------
-    pool_n = min(K, 256)
+    pool_n = min(max(K, 160), 256)          # >= 160 distinct batches: the pool (>= 128 MB at cfg2) exceeds the 126 MB L2
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     pool = torch.empty((pool_n, local_n, total), device=dev)
     for k, (lo, hi) in enumerate(cfg['ranges']):

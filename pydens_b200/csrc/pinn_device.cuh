@@ -25,6 +25,19 @@
 #define PINN_HD inline
 #define PINN_D  inline
 struct float4 { float x, y, z, w; };      // host emulation build only
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+// Packed FP32x2 arithmetic: Blackwell's FFMA2 / FMUL2 do two fp32 operations per issued instruction
+// (the scalar operand is broadcast by the instruction itself).  The inner loops keep their accumulators
+// as pairs of neighbouring output units, which halves the FMA instruction count.
+#if defined(__CUDA_ARCH__)
+#define PINN_FFMA2(a2, s, c2) __ffma2_rn((a2), make_float2((s), (s)), (c2))
+#define PINN_FMUL2(a2, s)     __fmul2_rn((a2), make_float2((s), (s)))
+#else
+#define PINN_FFMA2(a2, s, c2) make_float2(fmaf((a2).x, (s), (c2).x), fmaf((a2).y, (s), (c2).y))
+#define PINN_FMUL2(a2, s)     make_float2((a2).x * (s), (a2).y * (s))
 #endif
 
 namespace pinn {
@@ -219,13 +232,13 @@ PINN_HD void load_post_jet(const float* __restrict__ row, int RS, const ActC& k,
 template <int NF, int NS, int NB>
 PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
                               int n_in, const float* __restrict__ in_rows, int RS, const ActC& in_act,
-                              float (&acc)[NB * 4][1 + NF + NS]) {
+                              float2 (&acc)[NB * 2][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
-    for (int j = 0; j < NB * 4; ++j) {
-        acc[j][0] = bias[j];
+    for (int j = 0; j < NB * 2; ++j) {
+        acc[j][0] = make_float2(bias[2 * j], bias[2 * j + 1]);
 #pragma unroll
-        for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
+        for (int c = 1; c < C; ++c) acc[j][c] = make_float2(0.0f, 0.0f);
     }
 #pragma unroll 1
     for (int k = 0; k < n_in; ++k) {
@@ -234,13 +247,12 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
         const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
 #pragma unroll
         for (int g = 0; g < NB; ++g) {
-            float4 w = wrow[g];
+            const float4 w = wrow[g];
+            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                acc[4 * g + 0][c] = fmaf(w.x, a[c], acc[4 * g + 0][c]);
-                acc[4 * g + 1][c] = fmaf(w.y, a[c], acc[4 * g + 1][c]);
-                acc[4 * g + 2][c] = fmaf(w.z, a[c], acc[4 * g + 2][c]);
-                acc[4 * g + 3][c] = fmaf(w.w, a[c], acc[4 * g + 3][c]);
+                acc[2 * g + 0][c] = PINN_FFMA2(w01, a[c], acc[2 * g + 0][c]);
+                acc[2 * g + 1][c] = PINN_FFMA2(w23, a[c], acc[2 * g + 1][c]);
             }
         }
     }
@@ -251,13 +263,13 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
 template <int NF, int NS, int NB>
 PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
                              int n_in, const float* __restrict__ coords, int RS, const float* __restrict__ dirv,
-                             float (&acc)[NB * 4][1 + NF + NS]) {
+                             float2 (&acc)[NB * 2][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
-    for (int j = 0; j < NB * 4; ++j) {
-        acc[j][0] = bias[j];
+    for (int j = 0; j < NB * 2; ++j) {
+        acc[j][0] = make_float2(bias[2 * j], bias[2 * j + 1]);
 #pragma unroll
-        for (int c = 1; c < C; ++c) acc[j][c] = 0.0f;
+        for (int c = 1; c < C; ++c) acc[j][c] = make_float2(0.0f, 0.0f);
     }
 #pragma unroll 1
     for (int k = 0; k < n_in; ++k) {
@@ -268,17 +280,14 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
         const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
 #pragma unroll
         for (int g = 0; g < NB; ++g) {
-            float4 w = wrow[g];
-            acc[4 * g + 0][0] = fmaf(w.x, x, acc[4 * g + 0][0]);
-            acc[4 * g + 1][0] = fmaf(w.y, x, acc[4 * g + 1][0]);
-            acc[4 * g + 2][0] = fmaf(w.z, x, acc[4 * g + 2][0]);
-            acc[4 * g + 3][0] = fmaf(w.w, x, acc[4 * g + 3][0]);
+            const float4 w = wrow[g];
+            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+            acc[2 * g + 0][0] = PINN_FFMA2(w01, x, acc[2 * g + 0][0]);
+            acc[2 * g + 1][0] = PINN_FFMA2(w23, x, acc[2 * g + 1][0]);
 #pragma unroll
             for (int d = 0; d < NF; ++d) {
-                acc[4 * g + 0][1 + d] = fmaf(w.x, vd[d], acc[4 * g + 0][1 + d]);
-                acc[4 * g + 1][1 + d] = fmaf(w.y, vd[d], acc[4 * g + 1][1 + d]);
-                acc[4 * g + 2][1 + d] = fmaf(w.z, vd[d], acc[4 * g + 2][1 + d]);
-                acc[4 * g + 3][1 + d] = fmaf(w.w, vd[d], acc[4 * g + 3][1 + d]);
+                acc[2 * g + 0][1 + d] = PINN_FFMA2(w01, vd[d], acc[2 * g + 0][1 + d]);
+                acc[2 * g + 1][1 + d] = PINN_FFMA2(w23, vd[d], acc[2 * g + 1][1 + d]);
             }
         }
     }
@@ -287,17 +296,18 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
 // Store a block of freshly computed pre-activation jets: channel 0 goes through act_store().
 template <int NF, int NS, int NB>
 PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, int j0, int n_out,
-                         const float (&acc)[NB * 4][1 + NF + NS]) {
+                         const float2 (&acc)[NB * 2][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
     for (int j = 0; j < NB * 4; ++j) {
-        const float a = act_store(act, acc[j][0]);
+        const float z = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+        const float a = act_store(act, z);
         const bool ok = j0 + j < n_out;
         float* row = out_rows + (size_t)(ok ? j0 + j : j0) * C * RS;
         if (ok) row[0] = a;
 #pragma unroll
         for (int c = 1; c < C; ++c)
-            if (ok) row[(size_t)c * RS] = acc[j][c];
+            if (ok) row[(size_t)c * RS] = (j & 1) ? acc[j / 2][c].y : acc[j / 2][c].x;
     }
 }
 
@@ -317,7 +327,7 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
         if (nb > NBMAX) nb = NBMAX;
 #define PINN_FWD_CASE(NB)                                                                           \
         {                                                                                           \
-            float acc[NB * 4][1 + NF + NS];                                                         \
+            float2 acc[NB * 2][1 + NF + NS];                                                        \
             if (in_is_coords)                                                                       \
                 fwd_block_input<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,    \
                                             dirv, acc);                                             \
@@ -728,29 +738,38 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
     const int n_cols = L.n_in + 1;                        // + bias column
 #pragma unroll 1
     for (int m0 = 0; m0 < n_cols; m0 += JB) {
-        float post[JB][C];
+        // neighbouring input units are kept as pairs: one FFMA2 serves two of them
+        float2 post[JB / 2][C];
 #pragma unroll
-        for (int mm = 0; mm < JB; ++mm) {
-            const int m = m0 + mm;
-            const int mc = m < L.n_in ? m : L.n_in - 1;
-            load_post_jet<NF, NS>(load_rows + (size_t)mc * C * RS, RS, load_act, post[mm]);
-            if (m == L.n_in) {                            // bias column: jet (1, 0, …, 0)
-                post[mm][0] = 1.0f;
+        for (int h = 0; h < JB / 2; ++h) {
+            float pa[2][C];
 #pragma unroll
-                for (int c = 1; c < C; ++c) post[mm][c] = 0.0f;
+            for (int q = 0; q < 2; ++q) {
+                const int m = m0 + 2 * h + q;
+                const int mc = m < L.n_in ? m : L.n_in - 1;
+                load_post_jet<NF, NS>(load_rows + (size_t)mc * C * RS, RS, load_act, pa[q]);
+                if (m == L.n_in) {                        // bias column: jet (1, 0, …, 0)
+                    pa[q][0] = 1.0f;
+#pragma unroll
+                    for (int c = 1; c < C; ++c) pa[q][c] = 0.0f;
+                }
             }
+#pragma unroll
+            for (int c = 0; c < C; ++c) post[h][c] = make_float2(pa[0][c], pa[1][c]);
         }
-        float acc[JB][C];
+        float2 acc[JB / 2][C];
 #pragma unroll
-        for (int mm = 0; mm < JB; ++mm)
+        for (int h = 0; h < JB / 2; ++h)
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[mm][c] = 0.0f;
+            for (int c = 0; c < C; ++c) acc[h][c] = make_float2(0.0f, 0.0f);
         if (SKIP && adj_in) {                             // the layer below also feeds a skip connection
 #pragma unroll
-            for (int mm = 0; mm < JB; ++mm) {
-                const int mc = m0 + mm < L.n_in ? m0 + mm : L.n_in - 1;
+            for (int h = 0; h < JB / 2; ++h) {
+                const int ma = m0 + 2 * h < L.n_in ? m0 + 2 * h : L.n_in - 1;
+                const int mb = m0 + 2 * h + 1 < L.n_in ? m0 + 2 * h + 1 : L.n_in - 1;
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[mm][c] = adj_in[((size_t)mc * C + c) * RS];
+                for (int c = 0; c < C; ++c)
+                    acc[h][c] = make_float2(adj_in[((size_t)ma * C + c) * RS], adj_in[((size_t)mb * C + c) * RS]);
             }
         }
 
@@ -766,17 +785,19 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
 #pragma unroll
                 for (int c = 0; c < C; ++c) zb[c] = row[(size_t)c * RS];
                 const float4* wrow = reinterpret_cast<const float4*>(W + (size_t)j * L.n_in_p8 + m0);
-                float4 w0 = wrow[0], w1 = wrow[1];
-                float w[JB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float4 w0 = wrow[0], w1 = wrow[1];
+                const float2 w[JB / 2] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w),
+                                          make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-                for (int mm = 0; mm < JB; ++mm) {
-                    float e = zb[0] * post[mm][0];
+                for (int h = 0; h < JB / 2; ++h) {
+                    float2 e = PINN_FMUL2(post[h][0], zb[0]);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        acc[mm][c] = fmaf(w[mm], zb[c], acc[mm][c]);
-                        if (c > 0) e = fmaf(zb[c], post[mm][c], e);
+                        acc[h][c] = PINN_FFMA2(w[h], zb[c], acc[h][c]);
+                        if (c > 0) e = PINN_FFMA2(post[h][c], zb[c], e);
                     }
-                    v[jj * JB + mm] = e;
+                    v[jj * JB + 2 * h] = e.x;
+                    v[jj * JB + 2 * h + 1] = e.y;
                 }
             }
             emit_entries<JJ * JB>(v, [&](int e, float t) {
@@ -793,8 +814,10 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
 #pragma unroll
             for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
             ActD f = act_from_stored(below, pre[0]);
-            float zb[C];
-            act_adjoint<NF, NS>(f, pre, acc[mm], zb);
+            float ab[C], zb[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) ab[c] = (mm & 1) ? acc[mm / 2][c].y : acc[mm / 2][c].x;
+            act_adjoint<NF, NS>(f, pre, ab, zb);
             float* wrow = ok ? in_rows + (size_t)(m0 + mm) * C * RS : dump_rows;   // masked-off units: dump rows
 #pragma unroll
             for (int c = 0; c < C; ++c) wrow[(size_t)c * RS] = zb[c];
@@ -802,7 +825,7 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
                 float* srow = adj_out + (size_t)(ok ? m0 + mm : 0) * C * RS;
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    if (ok) srow[(size_t)c * RS] = acc[mm][c];
+                    if (ok) srow[(size_t)c * RS] = ab[c];
             }
         }
     }
