@@ -240,7 +240,11 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
 #pragma unroll
         for (int c = 1; c < C; ++c) acc[j][c] = make_float2(0.0f, 0.0f);
     }
-#pragma unroll 1
+    // many-channel problems keep their per-point state in global memory: more iterations in flight overlap
+    // the load latency there (measured: cfg5 -10 %), while for the shared-memory-resident narrow problems
+    // unrolling only costs instruction-cache reach (cfg2 +7 %)
+    constexpr int UNR = (C >= 8) ? 4 : ((C >= 6) ? 2 : 1);
+#pragma unroll UNR
     for (int k = 0; k < n_in; ++k) {
         float a[C];
         load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);

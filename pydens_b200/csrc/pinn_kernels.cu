@@ -206,6 +206,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         p->regs = fa.numRegs;
         int nw = var->maxt / 32;
         if (65536 / (fa.numRegs * 32) < nw) nw = 65536 / (fa.numRegs * 32);
+        { const char* e2 = getenv("PINN_GMEM_WARPS"); if (e2 && atoi(e2) >= 1 && atoi(e2) <= nw) nw = atoi(e2); }   // experiments
         int nwacc = nw;
         SmemLayout SL = smem_layout(h.weights_floats, n_out_floats, nwacc, h.n_params);
         if (SL.total_f * 4 > budget) { nwacc = 1; SL = smem_layout(h.weights_floats, n_out_floats, 1, h.n_params); }
