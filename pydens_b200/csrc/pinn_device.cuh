@@ -35,9 +35,13 @@ inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return
 #if defined(__CUDA_ARCH__)
 #define PINN_FFMA2(a2, s, c2) __ffma2_rn((a2), make_float2((s), (s)), (c2))
 #define PINN_FMUL2(a2, s)     __fmul2_rn((a2), make_float2((s), (s)))
+#define PINN_FFMA2V(a2, b2, c2) __ffma2_rn((a2), (b2), (c2))
+#define PINN_FMUL2V(a2, b2)     __fmul2_rn((a2), (b2))
 #else
 #define PINN_FFMA2(a2, s, c2) make_float2(fmaf((a2).x, (s), (c2).x), fmaf((a2).y, (s), (c2).y))
 #define PINN_FMUL2(a2, s)     make_float2((a2).x * (s), (a2).y * (s))
+#define PINN_FFMA2V(a2, b2, c2) make_float2(fmaf((a2).x, (b2).x, (c2).x), fmaf((a2).y, (b2).y, (c2).y))
+#define PINN_FMUL2V(a2, b2)     make_float2((a2).x * (b2).x, (a2).y * (b2).y)
 #endif
 
 namespace pinn {
@@ -658,6 +662,34 @@ PINN_HD void act_adjoint(const ActD& f, const float (&pre)[1 + NF + NS], const f
     zb[0] = z0;
 }
 
+// The same adjoint for TWO neighbouring units at once (every operation is element-wise, so the pair
+// rides on packed FP32x2 instructions): pre/ab/zb hold (unit, unit+1) pairs per channel.
+template <int NF, int NS>
+PINN_HD void act_adjoint2(const ActC& k, const float2 (&pre)[1 + NF + NS], const float2 (&ab)[1 + NF + NS],
+                          float2 (&zb)[1 + NF + NS]) {
+    const float2 a = pre[0];
+    const float2 s1 = PINN_FFMA2V(PINN_FFMA2(a, k.c2, make_float2(k.c1, k.c1)), a, make_float2(k.c0, k.c0));
+    const float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(a, k.d1, make_float2(k.d0, k.d0)));
+    const float2 s3 = PINN_FMUL2V(s1, PINN_FFMA2V(PINN_FFMA2(a, k.e2, make_float2(k.e1, k.e1)), a, make_float2(k.e0, k.e0)));
+    float2 z0 = PINN_FMUL2V(s1, ab[0]);
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        const float2 zd = pre[1 + d];
+        const float2 t = PINN_FMUL2V(s2, zd);
+        z0 = PINN_FFMA2V(t, ab[1 + d], z0);
+        float2 zdb = PINN_FMUL2V(s1, ab[1 + d]);
+        if (d < NS) {
+            const float2 q = ab[1 + NF + d];
+            zdb = PINN_FFMA2V(PINN_FMUL2(t, 2.0f), q, zdb);
+            const float2 w = PINN_FFMA2V(PINN_FMUL2V(s3, zd), zd, PINN_FMUL2V(s2, pre[1 + NF + d]));
+            z0 = PINN_FFMA2V(w, q, z0);
+            zb[1 + NF + d] = PINN_FMUL2V(s1, q);
+        }
+        zb[1 + d] = zdb;
+    }
+    zb[0] = z0;
+}
+
 #if defined(__CUDA_ARCH__)
 // Sum NV per-lane values over the 32 lanes of a warp with a transposing butterfly: on return the
 // lane with (lane % NV) == e holds the total of entry e.  31 shuffles for NV == 32.
@@ -809,27 +841,28 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
                 sink.add_if(j < L.n_out && m <= L.n_in, m < L.n_in ? L.w_off + j * L.n_in + m : L.b_off + j, t);
             });
         }
-        // adjoints of the layer below: through its activation, stored in place
+        // adjoints of the layer below: through its activation (two units per packed op), stored in place
 #pragma unroll
-        for (int mm = 0; mm < JB; ++mm) {
-            const bool ok = m0 + mm < L.n_in;
-            const float* row = in_rows + (size_t)(ok ? m0 + mm : 0) * C * RS;
-            float pre[C];
+        for (int h = 0; h < JB / 2; ++h) {
+            const bool oka = m0 + 2 * h < L.n_in, okb = m0 + 2 * h + 1 < L.n_in;
+            const float* rowa = in_rows + (size_t)(oka ? m0 + 2 * h : 0) * C * RS;
+            const float* rowb = in_rows + (size_t)(okb ? m0 + 2 * h + 1 : 0) * C * RS;
+            float2 pre[C], zb[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) pre[c] = row[(size_t)c * RS];
-            ActD f = act_from_stored(below, pre[0]);
-            float ab[C], zb[C];
+            for (int c = 0; c < C; ++c) pre[c] = make_float2(rowa[(size_t)c * RS], rowb[(size_t)c * RS]);
+            act_adjoint2<NF, NS>(below, pre, acc[h], zb);
+            float* wa = oka ? in_rows + (size_t)(m0 + 2 * h) * C * RS : dump_rows;      // masked-off units: dump rows
+            float* wb = okb ? in_rows + (size_t)(m0 + 2 * h + 1) * C * RS : dump_rows;
 #pragma unroll
-            for (int c = 0; c < C; ++c) ab[c] = (mm & 1) ? acc[mm / 2][c].y : acc[mm / 2][c].x;
-            act_adjoint<NF, NS>(f, pre, ab, zb);
-            float* wrow = ok ? in_rows + (size_t)(m0 + mm) * C * RS : dump_rows;   // masked-off units: dump rows
-#pragma unroll
-            for (int c = 0; c < C; ++c) wrow[(size_t)c * RS] = zb[c];
+            for (int c = 0; c < C; ++c) { wa[(size_t)c * RS] = zb[c].x; wb[(size_t)c * RS] = zb[c].y; }
             if (SKIP && adj_out) {                        // residual layer: its skip source needs this adjoint too
-                float* srow = adj_out + (size_t)(ok ? m0 + mm : 0) * C * RS;
+                float* sa = adj_out + (size_t)(oka ? m0 + 2 * h : 0) * C * RS;
+                float* sb = adj_out + (size_t)(okb ? m0 + 2 * h + 1 : 0) * C * RS;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    if (ok) srow[(size_t)c * RS] = ab[c];
+                for (int c = 0; c < C; ++c) {
+                    if (oka) sa[(size_t)c * RS] = acc[h][c].x;
+                    if (okb) sb[(size_t)c * RS] = acc[h][c].y;
+                }
             }
         }
     }
