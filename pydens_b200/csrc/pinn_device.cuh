@@ -228,6 +228,25 @@ PINN_HD void load_post_jet(const float* __restrict__ row, int RS, const ActC& k,
     }
 }
 
+// The same for TWO units at once (rows of units A and B), on packed FP32x2 operations.
+template <int NF, int NS>
+PINN_HD void load_post_jet2(const float* __restrict__ rowa, const float* __restrict__ rowb, int RS, const ActC& k,
+                            float2 (&a)[1 + NF + NS]) {
+    const float2 av = make_float2(rowa[0], rowb[0]);
+    const float2 s1 = PINN_FFMA2V(PINN_FFMA2(av, k.c2, make_float2(k.c1, k.c1)), av, make_float2(k.c0, k.c0));
+    const float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(av, k.d1, make_float2(k.d0, k.d0)));
+    a[0] = av;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        const float2 zd = make_float2(rowa[(1 + d) * RS], rowb[(1 + d) * RS]);
+        a[1 + d] = PINN_FMUL2V(s1, zd);
+        if (d < NS) {
+            const float2 zdd = make_float2(rowa[(1 + NF + d) * RS], rowb[(1 + NF + d) * RS]);
+            a[1 + NF + d] = PINN_FFMA2V(PINN_FMUL2V(s2, zd), zd, PINN_FMUL2V(s1, zdd));
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Forward: one block of NB*4 output units of a linear layer, all jet channels at once.
 // Wt is the forward layout [n_in][n_out_p4]; weights are read with 128-bit broadcast loads and
@@ -703,11 +722,19 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 #pragma unroll
     for (int s = (NV / 2 < 16 ? NV / 2 : 16); s >= 1; s >>= 1) {
         bool up = (lane & s) != 0;
+        if (s >= 2) {                                     // two exchanges per packed add
 #pragma unroll
-        for (int i = 0; i < s; ++i) {
-            float send = up ? v[i] : v[i + s];
-            float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            for (int i = 0; i < s; i += 2) {
+                float send0 = up ? v[i] : v[i + s], send1 = up ? v[i + 1] : v[i + 1 + s];
+                float2 keep = make_float2(up ? v[i + s] : v[i], up ? v[i + 1 + s] : v[i + 1]);
+                float2 got = make_float2(__shfl_xor_sync(0xffffffffu, send0, s), __shfl_xor_sync(0xffffffffu, send1, s));
+                keep = __fadd2_rn(keep, got);
+                v[i] = keep.x; v[i + 1] = keep.y;
+            }
+        } else {
+            float send = up ? v[0] : v[1];
+            float keep = up ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         }
     }
     return v[0];
@@ -778,20 +805,20 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
         float2 post[JB / 2][C];
 #pragma unroll
         for (int h = 0; h < JB / 2; ++h) {
-            float pa[2][C];
+            const int ma = m0 + 2 * h, mb = ma + 1;
+            const int ca = ma < L.n_in ? ma : L.n_in - 1, cb = mb < L.n_in ? mb : L.n_in - 1;
+            load_post_jet2<NF, NS>(load_rows + (size_t)ca * C * RS, load_rows + (size_t)cb * C * RS, RS, load_act,
+                                   post[h]);
+            if (ma == L.n_in) {                           // bias column: jet (1, 0, …, 0)
+                post[h][0].x = 1.0f;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int m = m0 + 2 * h + q;
-                const int mc = m < L.n_in ? m : L.n_in - 1;
-                load_post_jet<NF, NS>(load_rows + (size_t)mc * C * RS, RS, load_act, pa[q]);
-                if (m == L.n_in) {                        // bias column: jet (1, 0, …, 0)
-                    pa[q][0] = 1.0f;
-#pragma unroll
-                    for (int c = 1; c < C; ++c) pa[q][c] = 0.0f;
-                }
+                for (int c = 1; c < C; ++c) post[h][c].x = 0.0f;
             }
+            if (mb == L.n_in) {
+                post[h][0].y = 1.0f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) post[h][c] = make_float2(pa[0][c], pa[1][c]);
+                for (int c = 1; c < C; ++c) post[h][c].y = 0.0f;
+            }
         }
         float2 acc[JB / 2][C];
 #pragma unroll
