@@ -200,6 +200,31 @@ PINN_HD float act_store(const ActC& k, float z) {
     return k.ident ? z : t;
 }
 
+// act_store for two neighbouring units: the polynomial branch and the final blend run packed.
+PINN_HD float2 act_store2(const ActC& k, float2 z) {
+    const float2 x = PINN_FMUL2(z, k.q);
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 x2 = PINN_FMUL2V(ax, ax);
+    float2 p = PINN_FFMA2(x2, 1.6022265e-2f, make_float2(-5.2653320e-2f, -5.2653320e-2f));
+    p = PINN_FFMA2V(p, x2, make_float2(1.3314733e-1f, 1.3314733e-1f));
+    p = PINN_FFMA2V(p, x2, make_float2(-3.3332834e-1f, -3.3332834e-1f));
+    const float2 small = PINN_FFMA2V(PINN_FMUL2V(p, x2), ax, ax);
+#if defined(__CUDA_ARCH__)
+    float e0, e1;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ax.x * 2.8853900817779268f));
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ax.y * 2.8853900817779268f));
+    const float2 r = make_float2(__frcp_rn(e0 + 1.0f), __frcp_rn(e1 + 1.0f));
+#else
+    const float2 r = make_float2(1.0f / (exp2f(ax.x * 2.8853900817779268f) + 1.0f),
+                                 1.0f / (exp2f(ax.y * 2.8853900817779268f) + 1.0f));
+#endif
+    const float2 big = PINN_FFMA2(r, -2.0f, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(copysignf(ax.x < 0.55f ? small.x : big.x, x.x),
+                                 copysignf(ax.y < 0.55f ? small.y : big.y, x.y));
+    const float2 out = PINN_FFMA2(t, k.p, make_float2(k.r, k.r));
+    return k.ident ? z : out;
+}
+
 PINN_HD ActD act_from_stored(const ActC& k, float a) {
     ActD r;
     r.a = a;
@@ -326,15 +351,18 @@ PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, 
                          const float2 (&acc)[NB * 2][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
-    for (int j = 0; j < NB * 4; ++j) {
-        const float z = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-        const float a = act_store(act, z);
-        const bool ok = j0 + j < n_out;
-        float* row = out_rows + (size_t)(ok ? j0 + j : j0) * C * RS;
-        if (ok) row[0] = a;
+    for (int h = 0; h < NB * 2; ++h) {
+        const float2 a = act_store2(act, acc[h][0]);
 #pragma unroll
-        for (int c = 1; c < C; ++c)
-            if (ok) row[(size_t)c * RS] = (j & 1) ? acc[j / 2][c].y : acc[j / 2][c].x;
+        for (int q = 0; q < 2; ++q) {
+            const int j = 2 * h + q;
+            const bool ok = j0 + j < n_out;
+            float* row = out_rows + (size_t)(ok ? j0 + j : j0) * C * RS;
+            if (ok) row[0] = q ? a.y : a.x;
+#pragma unroll
+            for (int c = 1; c < C; ++c)
+                if (ok) row[(size_t)c * RS] = q ? acc[h][c].y : acc[h][c].x;
+        }
     }
 }
 
@@ -920,10 +948,16 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
                                const float* __restrict__ coords, int RS, const float* __restrict__ dirv,
                                const GradSink& sink) {
     constexpr int C = 1 + NF + NS;
-    float x[PINN_MAX_DIMS];
+    float2 x[PINN_MAX_DIMS / 2];
+    float2 dv[NF > 0 ? NF : 1][PINN_MAX_DIMS / 2];
 #pragma unroll
-    for (int m = 0; m < PINN_MAX_DIMS; ++m)
-        x[m] = (m < L.n_in) ? coords[(size_t)m * RS] : (m == L.n_in ? 1.0f : 0.0f);
+    for (int h = 0; h < PINN_MAX_DIMS / 2; ++h) {
+        const int ma = 2 * h, mb = 2 * h + 1;
+        x[h] = make_float2((ma < L.n_in) ? coords[(size_t)ma * RS] : (ma == L.n_in ? 1.0f : 0.0f),
+                           (mb < L.n_in) ? coords[(size_t)mb * RS] : (mb == L.n_in ? 1.0f : 0.0f));
+#pragma unroll
+        for (int d = 0; d < NF; ++d) dv[d][h] = make_float2(dirv[d * PINN_MAX_DIMS + ma], dirv[d * PINN_MAX_DIMS + mb]);
+    }
 #pragma unroll 1
     for (int j0 = 0; j0 < L.n_out; j0 += 4) {
         float v[4 * PINN_MAX_DIMS];
@@ -935,11 +969,12 @@ PINN_HD void wgrad_input_layer(const DevLayer& L, const float* __restrict__ out_
 #pragma unroll
             for (int c = 0; c < 1 + NF; ++c) zb[c] = row[(size_t)c * RS];
 #pragma unroll
-            for (int m = 0; m < PINN_MAX_DIMS; ++m) {
-                float e = zb[0] * x[m];
+            for (int h = 0; h < PINN_MAX_DIMS / 2; ++h) {
+                float2 e = PINN_FMUL2(x[h], zb[0]);
 #pragma unroll
-                for (int d = 0; d < NF; ++d) e = fmaf(dirv[d * PINN_MAX_DIMS + m], zb[1 + d], e);
-                v[jj * PINN_MAX_DIMS + m] = e;
+                for (int d = 0; d < NF; ++d) e = PINN_FFMA2(dv[d][h], zb[1 + d], e);
+                v[jj * PINN_MAX_DIMS + 2 * h] = e.x;
+                v[jj * PINN_MAX_DIMS + 2 * h + 1] = e.y;
             }
         }
         emit_entries<4 * PINN_MAX_DIMS>(v, [&](int e, float t) {
