@@ -17,7 +17,7 @@ import torch
 from . import _native
 
 _GRAPH_MIN_ITERS = 8
-_HOST_GRAPH_MIN_ITERS = 2000        # host-sampler mode: 4 captures (~20 ms each) only pay off on long fits
+_HOST_GRAPH_MIN_ITERS = 64          # host-sampler mode: one capture per staging buffer
 
 
 def _dist():
@@ -25,6 +25,32 @@ def _dist():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None
+
+
+def capture_graph(device, body, pool=None):
+    """ Capture `body()` into a CUDA graph on a side stream.  Unlike the `torch.cuda.graph` context manager this
+    does not run the garbage collector and does not empty the allocator cache, which is what makes a capture
+    cost ~20 ms there; a fit only pays a millisecond or two here. """
+    graph = torch.cuda.CUDAGraph()
+    current = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(current)
+    with torch.cuda.stream(side):
+        try:
+            if pool is not None:
+                graph.capture_begin(pool=pool)
+            else:
+                graph.capture_begin()
+            body()
+            graph.capture_end()
+        except Exception:
+            try:
+                graph.capture_end()
+            except Exception:                       # noqa: BLE001
+                pass
+            raise
+    current.wait_stream(side)
+    return graph
 
 
 def shard_batch(batch_size, world, rank):
@@ -232,6 +258,7 @@ class FusedEngine:
             events = [torch.cuda.Event() for _ in range(n_stage)]          # H2D of buffer k has completed
             free_ev = [torch.cuda.Event() for _ in range(n_stage)]         # compute no longer reads dev_pts[k]
             copy_stream = torch.cuda.Stream(device=self.device)
+            d2h_stream = torch.cuda.Stream(device=self.device)
             dev_pts = [torch.empty((local_n, total), dtype=torch.float32, device=self.device) for _ in range(n_stage)]
             zero_host = torch.zeros(max(niters, 1), dtype=torch.float32).pin_memory()
 
@@ -263,10 +290,11 @@ class FusedEngine:
             graph = None
             try:
                 torch.cuda.synchronize(self.device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+
+                def body():
                     for k in range(per_graph):
                         one_step(1 + k)
+                graph = capture_graph(self.device, body)
             except Exception:                         # capture unsupported here: plain launches
                 graph = None
                 torch.cuda.synchronize(self.device)
@@ -300,7 +328,12 @@ class FusedEngine:
                     else:
                         one_step(done + i, dev_pts[k])
                     free_ev[k].record(cur)
-                    zero_host[done + i:done + i + 1].copy_(self.out[loss_idx:loss_idx + 1], non_blocking=True)
+                    # the step's loss goes to the host every step (as in the reference, :464) — from the device
+                    # ring and on its own stream, so that the read-back never sits between two steps
+                    with torch.cuda.stream(d2h_stream):
+                        d2h_stream.wait_event(free_ev[k])
+                        r = (start + done + i) % ring.numel()
+                        zero_host[done + i:done + i + 1].copy_(ring[r:r + 1], non_blocking=True)
                     # after the first (eager) step the optimizer state exists: capture the compute part of the
                     # step once per staging buffer, so that every later step is copy -> replay -> loss read
                     if (i == 0 and stage_graphs is None and capturable and not nums and niters - done >= _HOST_GRAPH_MIN_ITERS
@@ -309,10 +342,8 @@ class FusedEngine:
                             torch.cuda.synchronize(self.device)
                             graphs = []
                             for kk in range(len(pinned)):
-                                g = torch.cuda.CUDAGraph()
-                                with torch.cuda.graph(g):
-                                    one_step(0, dev_pts[kk])
-                                graphs.append(g)
+                                graphs.append(capture_graph(self.device, lambda kk=kk: one_step(0, dev_pts[kk]),
+                                                            pool=graphs[0].pool() if graphs else None))
                             stage_graphs = graphs
                         except Exception:               # capture unsupported here: keep plain launches
                             stage_graphs = None
