@@ -54,7 +54,10 @@ extern "C" {
 #define PINN_ACT_NONE       0
 #define PINN_ACT_TANH       1
 #define PINN_ACT_SIGMOID    2
-#define PINN_ACT_SIN        3
+#define PINN_ACT_SIN        3   /* sin z (batchflow-style `Sin` callable, model_torch.py:150-151) */
+#define PINN_ACT_SOFTPLUS   4   /* nn.Softplus() with default beta / threshold     */
+#define PINN_ACT_SILU       5   /* nn.SiLU()                                       */
+#define PINN_ACT_GELU       6   /* nn.GELU() (erf form)                            */
 
 /* expression-program opcodes: a tiny register machine evaluated once per collocation
  * point.  Programs are produced on the host by tracing the user's `equation` /

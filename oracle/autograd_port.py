@@ -117,14 +117,18 @@ class Problem:
     # ---- model ----
     def net(self, xs_concat):
         h = xs_concat
-        act = getattr(torch.nn, self.activation)()
-        saved, i_f = [], 0
+        # `activation`: an nn.* name, a module class, or a sequence of those, one per 'a' (model_torch.py:150-151)
+        n_a = self.layout.count('a')
+        spec = list(self.activation) if isinstance(self.activation, (list, tuple)) else [self.activation] * n_a
+        acts = [getattr(torch.nn, a)() if isinstance(a, str) else a() for a in spec]
+        saved, i_f, i_a = [], 0, 0
         for letter in self.layout:
             if letter == 'f':
                 h = torch.nn.functional.linear(h, self.weights[i_f], self.biases[i_f])
                 i_f += 1
             elif letter == 'a':
-                h = act(h)
+                h = acts[i_a](h)
+                i_a += 1
             elif letter == 'R':
                 saved.append(h)
             elif letter == '+':

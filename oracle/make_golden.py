@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference):
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [problem names …]
 
 It imports `/root/reference/pydens/model_torch.py` as is (through oracle/batchflow_standin, the
 stand-in for the un-vendored `batchflow`), builds every problem of tests/problems.py with the
@@ -100,7 +100,10 @@ def evaluate(solver, pts):
 def main():
     outdir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(outdir, exist_ok=True)
+    only = set(sys.argv[1:])                              # optional: problem names to (re)generate
     for name, cfg in P.PROBLEMS.items():
+        if only and name not in only:
+            continue
         var_names = list(cfg.get('variables', {}))
         solver = build(name)
         pts = P.make_points(name, P.GOLDEN_BATCH[name], seed=123)

@@ -9,7 +9,7 @@ import os
 ABI_VERSION = 7
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
-ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3}
+ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
 COL_UNIFORM, COL_NORMAL, COL_CONST = 0, 1, 2
 
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN, E_WORKSPACE = -1, -2, -3, -4, -5

@@ -160,13 +160,18 @@ PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_
 // tanh   : s1 = 1 - a^2,  s2 = -2 a s1,         s3 = s1 (-2 + 6 a^2)
 // sigmoid: s1 = a - a^2,  s2 = s1 (1 - 2 a),    s3 = s1 (1 - 6 a + 6 a^2)
 // (s1, s2, s3 = first, second, third derivative of the activation w.r.t. its argument.)
+//
+// Activations outside that family (sin, softplus, SiLU, GELU) keep the pre-activation z itself in channel 0
+// and rebuild (a, s1, s2, s3) from it wherever they are needed (act_terms_z): `zs` holds their id, 0 for the
+// polynomial family.  Only the general kernel variants (template flag GEN) compile that path.
 // ----------------------------------------------------------------------------------------------
 struct ActD { float a, s1, s2, s3; };
-struct ActC { float p, q, r, c0, c1, c2, d0, d1, e0, e1, e2; bool ident; };
+struct ActC { float p, q, r, c0, c1, c2, d0, d1, e0, e1, e2; bool ident; int zs; };
 
 PINN_HD ActC make_actc(int act) {
     const bool th = act == PINN_ACT_TANH, sg = act == PINN_ACT_SIGMOID;
     ActC k;
+    k.zs = (act >= PINN_ACT_SIN && act <= PINN_ACT_GELU) ? act : 0;
     k.ident = !(th || sg);
     k.p = sg ? 0.5f : 1.0f; k.q = sg ? 0.5f : 1.0f; k.r = sg ? 0.5f : 0.0f;
     k.c0 = sg ? 0.0f : 1.0f; k.c1 = sg ? 1.0f : 0.0f; k.c2 = (th || sg) ? -1.0f : 0.0f;
@@ -195,13 +200,57 @@ PINN_HD float tanh_acc(float x) {
     return copysignf(ax < 0.55f ? small : big, x);
 }
 
+// Value and first three derivatives of a z-stored activation at z.
+//   sin      : a = sin z,            s1 = cos z,  s2 = -a,  s3 = -s1
+//   softplus : a = log(1 + e^z),     s1 = sg(z),  s2 = s1 (1 - s1),  s3 = s2 (1 - 2 s1)         (sg = logistic)
+//   SiLU     : a = z sg,  with g1 = sg (1 - sg), g2 = g1 (1 - 2 sg), g3 = g2 (1 - 2 sg) - 2 g1^2:
+//              s1 = sg + z g1,  s2 = 2 g1 + z g2,  s3 = 3 g2 + z g3
+//   GELU     : a = z Phi(z) (erf form),  s1 = Phi + z phi,  s2 = phi (2 - z^2),  s3 = phi z (z^2 - 4)
+PINN_HD void act_terms_z(int kind, float z, float& a, float& s1, float& s2, float& s3) {
+    if (kind == PINN_ACT_SIN) {
+        float sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincosf(z, &sn, &cs);
+#else
+        sn = sinf(z); cs = cosf(z);
+#endif
+        a = sn; s1 = cs; s2 = -sn; s3 = -cs;
+    } else if (kind == PINN_ACT_GELU) {
+        const float phi = 0.3989422804014327f * expf(-0.5f * z * z);
+        const float Phi = 0.5f * erfcf(-0.7071067811865476f * z);
+        const float z2 = z * z;
+        a = z * Phi;
+        s1 = fmaf(z, phi, Phi);
+        s2 = phi * (2.0f - z2);
+        s3 = phi * z * (z2 - 4.0f);
+    } else {
+        const float sg = fmaf(0.5f, tanh_acc(0.5f * z), 0.5f);
+        const float g1 = sg * (1.0f - sg);
+        const float om = fmaf(-2.0f, sg, 1.0f);
+        const float g2 = g1 * om;
+        if (kind == PINN_ACT_SOFTPLUS) {
+            a = fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z)));
+            s1 = sg; s2 = g1; s3 = g2;
+        } else {                                          // SiLU
+            const float g3 = fmaf(g2, om, -2.0f * g1 * g1);
+            a = z * sg;
+            s1 = fmaf(z, g1, sg);
+            s2 = fmaf(z, g2, 2.0f * g1);
+            s3 = fmaf(z, g3, 3.0f * g2);
+        }
+    }
+}
+
+template <bool GEN = true>
 PINN_HD float act_store(const ActC& k, float z) {
     const float t = fmaf(k.p, tanh_acc(k.q * z), k.r);
-    return k.ident ? z : t;
+    return (k.ident || (GEN && k.zs)) ? z : t;
 }
 
 // act_store for two neighbouring units: the polynomial branch and the final blend run packed.
+template <bool GEN = true>
 PINN_HD float2 act_store2(const ActC& k, float2 z) {
+    if (GEN && k.zs) return z;                            // z-stored family: channel 0 keeps z
     const float2 x = PINN_FMUL2(z, k.q);
     const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
     const float2 x2 = PINN_FMUL2V(ax, ax);
@@ -227,6 +276,7 @@ PINN_HD float2 act_store2(const ActC& k, float2 z) {
 
 PINN_HD ActD act_from_stored(const ActC& k, float a) {
     ActD r;
+    if (k.zs) { act_terms_z(k.zs, a, r.a, r.s1, r.s2, r.s3); return r; }
     r.a = a;
     r.s1 = fmaf(fmaf(k.c2, a, k.c1), a, k.c0);
     r.s2 = r.s1 * fmaf(k.d1, a, k.d0);
@@ -236,11 +286,12 @@ PINN_HD ActD act_from_stored(const ActC& k, float a) {
 
 // Load the stored (pre-activation) jet of one hidden unit and turn it into the post-activation
 // jet that feeds the next linear layer:  a, a_d = s1*z_d, a_dd = s2*z_d^2 + s1*z_dd.
-template <int NF, int NS>
+template <int NF, int NS, bool GEN = true>
 PINN_HD void load_post_jet(const float* __restrict__ row, int RS, const ActC& k, float (&a)[1 + NF + NS]) {
-    const float av = row[0];
-    const float s1 = fmaf(fmaf(k.c2, av, k.c1), av, k.c0);
-    const float s2 = s1 * fmaf(k.d1, av, k.d0);
+    float av = row[0];
+    float s1 = fmaf(fmaf(k.c2, av, k.c1), av, k.c0);
+    float s2 = s1 * fmaf(k.d1, av, k.d0);
+    if (GEN && k.zs) { float s3; act_terms_z(k.zs, row[0], av, s1, s2, s3); }
     a[0] = av;
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
@@ -254,12 +305,18 @@ PINN_HD void load_post_jet(const float* __restrict__ row, int RS, const ActC& k,
 }
 
 // The same for TWO units at once (rows of units A and B), on packed FP32x2 operations.
-template <int NF, int NS>
+template <int NF, int NS, bool GEN = true>
 PINN_HD void load_post_jet2(const float* __restrict__ rowa, const float* __restrict__ rowb, int RS, const ActC& k,
                             float2 (&a)[1 + NF + NS]) {
-    const float2 av = make_float2(rowa[0], rowb[0]);
-    const float2 s1 = PINN_FFMA2V(PINN_FFMA2(av, k.c2, make_float2(k.c1, k.c1)), av, make_float2(k.c0, k.c0));
-    const float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(av, k.d1, make_float2(k.d0, k.d0)));
+    float2 av = make_float2(rowa[0], rowb[0]);
+    float2 s1 = PINN_FFMA2V(PINN_FFMA2(av, k.c2, make_float2(k.c1, k.c1)), av, make_float2(k.c0, k.c0));
+    float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(av, k.d1, make_float2(k.d0, k.d0)));
+    if (GEN && k.zs) {
+        float s3;
+        const float za = av.x, zb = av.y;
+        act_terms_z(k.zs, za, av.x, s1.x, s2.x, s3);
+        act_terms_z(k.zs, zb, av.y, s1.y, s2.y, s3);
+    }
     a[0] = av;
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
@@ -277,7 +334,7 @@ PINN_HD void load_post_jet2(const float* __restrict__ rowa, const float* __restr
 // Wt is the forward layout [n_in][n_out_p4]; weights are read with 128-bit broadcast loads and
 // every loaded weight feeds C FMAs.
 // ----------------------------------------------------------------------------------------------
-template <int NF, int NS, int NB>
+template <int NF, int NS, int NB, bool GEN = true>
 PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const float* __restrict__ bias,
                               int n_in, const float* __restrict__ in_rows, int RS, const ActC& in_act,
                               float2 (&acc)[NB * 2][1 + NF + NS]) {
@@ -295,7 +352,7 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
 #pragma unroll UNR
     for (int k = 0; k < n_in; ++k) {
         float a[C];
-        load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
+        load_post_jet<NF, NS, GEN>(in_rows + (size_t)k * C * RS, RS, in_act, a);
         const float4* wrow = reinterpret_cast<const float4*>(Wt + (size_t)k * wt_stride);
 #pragma unroll
         for (int g = 0; g < NB; ++g) {
@@ -346,13 +403,13 @@ PINN_HD void fwd_block_input(const float* __restrict__ Wt, int wt_stride, const 
 }
 
 // Store a block of freshly computed pre-activation jets: channel 0 goes through act_store().
-template <int NF, int NS, int NB>
+template <int NF, int NS, int NB, bool GEN = true>
 PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, int j0, int n_out,
                          const float2 (&acc)[NB * 2][1 + NF + NS]) {
     constexpr int C = 1 + NF + NS;
 #pragma unroll
     for (int h = 0; h < NB * 2; ++h) {
-        const float2 a = act_store2(act, acc[h][0]);
+        const float2 a = act_store2<GEN>(act, acc[h][0]);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int j = 2 * h + q;
@@ -367,7 +424,7 @@ PINN_HD void store_block(float* __restrict__ out_rows, int RS, const ActC& act, 
 }
 
 // One whole hidden (or input) linear layer, blocked over output units.
-template <int NF, int NS, int JF>
+template <int NF, int NS, int JF, bool GEN = true>
 PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
                        bool in_is_coords, int in_act_id, const float* __restrict__ dirv,
                        float* __restrict__ out_rows, int RS) {
@@ -387,9 +444,9 @@ PINN_HD void fwd_layer(const DevLayer& L, const float* __restrict__ sw, const fl
                 fwd_block_input<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,    \
                                             dirv, acc);                                             \
             else                                                                                    \
-                fwd_block_hidden<NF, NS, NB>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,   \
+                fwd_block_hidden<NF, NS, NB, GEN>(Wt + j0, L.n_out_p4, bias + j0, L.n_in, in_rows, RS,   \
                                              in_act, acc);                                          \
-            store_block<NF, NS, NB>(out_rows, RS, out_act, j0, L.n_out, acc);                         \
+            store_block<NF, NS, NB, GEN>(out_rows, RS, out_act, j0, L.n_out, acc);                    \
         }
         if (NBMAX >= 4 && nb == 4) PINN_FWD_CASE(4)
         else if (NBMAX >= 3 && nb == 3) PINN_FWD_CASE(3)
@@ -433,7 +490,7 @@ PINN_HD void skip_sum_pass(const DevPlan& P, int l, float* __restrict__ units, i
 }
 
 // Final linear layer (one output unit, no activation): the network jet N lands in registers.
-template <int NF, int NS>
+template <int NF, int NS, bool GEN = true>
 PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const float* __restrict__ in_rows,
                        bool in_is_coords, int in_act_id, const float* __restrict__ dirv, int RS,
                        float (&N)[1 + NF + NS]) {
@@ -453,7 +510,7 @@ PINN_HD void fwd_final(const DevLayer& L, const float* __restrict__ sw, const fl
 #pragma unroll 1
         for (int k = 0; k < L.n_in; ++k) {
             float a[C];
-            load_post_jet<NF, NS>(in_rows + (size_t)k * C * RS, RS, in_act, a);
+            load_post_jet<NF, NS, GEN>(in_rows + (size_t)k * C * RS, RS, in_act, a);
             float wk = w[k];
 #pragma unroll
             for (int c = 0; c < C; ++c) N[c] = fmaf(wk, a[c], N[c]);
@@ -711,13 +768,18 @@ PINN_HD void act_adjoint(const ActD& f, const float (&pre)[1 + NF + NS], const f
 
 // The same adjoint for TWO neighbouring units at once (every operation is element-wise, so the pair
 // rides on packed FP32x2 instructions): pre/ab/zb hold (unit, unit+1) pairs per channel.
-template <int NF, int NS>
+template <int NF, int NS, bool GEN = true>
 PINN_HD void act_adjoint2(const ActC& k, const float2 (&pre)[1 + NF + NS], const float2 (&ab)[1 + NF + NS],
                           float2 (&zb)[1 + NF + NS]) {
     const float2 a = pre[0];
-    const float2 s1 = PINN_FFMA2V(PINN_FFMA2(a, k.c2, make_float2(k.c1, k.c1)), a, make_float2(k.c0, k.c0));
-    const float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(a, k.d1, make_float2(k.d0, k.d0)));
-    const float2 s3 = PINN_FMUL2V(s1, PINN_FFMA2V(PINN_FFMA2(a, k.e2, make_float2(k.e1, k.e1)), a, make_float2(k.e0, k.e0)));
+    float2 s1 = PINN_FFMA2V(PINN_FFMA2(a, k.c2, make_float2(k.c1, k.c1)), a, make_float2(k.c0, k.c0));
+    float2 s2 = PINN_FMUL2V(s1, PINN_FFMA2(a, k.d1, make_float2(k.d0, k.d0)));
+    float2 s3 = PINN_FMUL2V(s1, PINN_FFMA2V(PINN_FFMA2(a, k.e2, make_float2(k.e1, k.e1)), a, make_float2(k.e0, k.e0)));
+    if (GEN && k.zs) {
+        float av;
+        act_terms_z(k.zs, a.x, av, s1.x, s2.x, s3.x);
+        act_terms_z(k.zs, a.y, av, s1.y, s2.y, s3.y);
+    }
     float2 z0 = PINN_FMUL2V(s1, ab[0]);
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
@@ -812,7 +874,7 @@ struct GradSink {
 // JJ = output units per reduction batch (4 normally, 1 for the single-output top layer).
 // No guards in the inner loops: rows/columns past the end are read from clamped (valid) addresses,
 // meet zero-padded weights, and their reduction entries are dropped at the sink.
-template <int NF, int NS, int JJ, bool SKIP>
+template <int NF, int NS, int JJ, bool SKIP, bool GEN = SKIP>
 PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restrict__ sw,
                        const float* __restrict__ out_rows, float* __restrict__ in_rows, int RS,
                        const GradSink& sink,
@@ -835,7 +897,7 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
         for (int h = 0; h < JB / 2; ++h) {
             const int ma = m0 + 2 * h, mb = ma + 1;
             const int ca = ma < L.n_in ? ma : L.n_in - 1, cb = mb < L.n_in ? mb : L.n_in - 1;
-            load_post_jet2<NF, NS>(load_rows + (size_t)ca * C * RS, load_rows + (size_t)cb * C * RS, RS, load_act,
+            load_post_jet2<NF, NS, GEN>(load_rows + (size_t)ca * C * RS, load_rows + (size_t)cb * C * RS, RS, load_act,
                                    post[h]);
             if (ma == L.n_in) {                           // bias column: jet (1, 0, …, 0)
                 post[h][0].x = 1.0f;
@@ -905,7 +967,7 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
             float2 pre[C], zb[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) pre[c] = make_float2(rowa[(size_t)c * RS], rowb[(size_t)c * RS]);
-            act_adjoint2<NF, NS>(below, pre, acc[h], zb);
+            act_adjoint2<NF, NS, GEN>(below, pre, acc[h], zb);
             float* wa = oka ? in_rows + (size_t)(m0 + 2 * h) * C * RS : dump_rows;      // masked-off units: dump rows
             float* wb = okb ? in_rows + (size_t)(m0 + 2 * h + 1) * C * RS : dump_rows;
 #pragma unroll
@@ -1010,8 +1072,8 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const DevLayer& L = P.layer[l];
         int in_act = PINN_ACT_NONE;
         const float* in_rows = (l == 0) ? coords : layer_output<GEN>(P, l - 1, units, C, RS, in_act);
-        fwd_layer<NF, NS, JF>(L, sw, in_rows, l == 0, in_act, &P.dir_vec[0][0],
-                              units + (size_t)L.unit_base * C * RS, RS);
+        fwd_layer<NF, NS, JF, GEN>(L, sw, in_rows, l == 0, in_act, &P.dir_vec[0][0],
+                                   units + (size_t)L.unit_base * C * RS, RS);
         if (GEN && L.skip_src >= 0) skip_sum_pass<NF, NS>(P, l, units, RS);
     }
     float N[C];
@@ -1019,7 +1081,7 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
         const DevLayer& L = P.layer[Ln - 1];
         int in_act = PINN_ACT_NONE;
         const float* in_rows = (Ln == 1) ? coords : layer_output<GEN>(P, Ln - 2, units, C, RS, in_act);
-        fwd_final<NF, NS>(L, sw, in_rows, Ln == 1, in_act, &P.dir_vec[0][0], RS, N);
+        fwd_final<NF, NS, GEN>(L, sw, in_rows, Ln == 1, in_act, &P.dir_vec[0][0], RS, N);
     }
 
     // ---- ansatz + residual ----
@@ -1082,8 +1144,8 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw /* weigh
             if (L.n_out == 1) bwd_layer<NF, NS, 1, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out, scr);
             else              bwd_layer<NF, NS, 4, true>(L, B.act, sw, out_rows, in_rows, RS, sink, load_rows, load_act, adj_in, adj_out, scr);
         } else {
-            if (L.n_out == 1) bwd_layer<NF, NS, 1, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
-            else              bwd_layer<NF, NS, 4, false>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
+            if (L.n_out == 1) bwd_layer<NF, NS, 1, false, GEN>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
+            else              bwd_layer<NF, NS, 4, false, GEN>(L, B.act, sw, out_rows, in_rows, RS, sink, in_rows, B.act, nullptr, nullptr, scr);
         }
     }
     {

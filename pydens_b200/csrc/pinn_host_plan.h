@@ -106,7 +106,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
         DevLayer& L = h.layer[l];
         L.n_in = s->widths[l]; L.n_out = s->widths[l + 1]; L.act = s->act[l];
         if (L.n_in < 1 || L.n_out < 1) PINN_PLAN_FAIL(PINN_E_INVALID, "layer %d width", l);
-        if (L.act < 0 || L.act > PINN_ACT_SIGMOID) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "layer %d: activation %d is not covered by the fused kernel", l, L.act);
+        if (L.act < 0 || L.act > PINN_ACT_GELU) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "layer %d: activation %d is not covered by the fused kernel", l, L.act);
         L.w_off = s->w_off[l]; L.b_off = s->b_off[l];
         if (L.w_off < 0 || L.w_off + L.n_in * L.n_out > s->n_params || L.b_off < 0 || L.b_off + L.n_out > s->n_params)
             PINN_PLAN_FAIL(PINN_E_INVALID, "layer %d offsets out of range", l);
@@ -131,6 +131,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     }
     h.general = h.ic_has_vars;
     for (int l = 0; l < Ln; ++l) if (h.layer[l].skip_src >= 0) h.general = 1;
+    for (int l = 0; l < Ln; ++l) if (h.layer[l].act >= PINN_ACT_SIN) h.general = 1;     // z-stored activations
     for (int d = 0; d < s->nf; ++d) if (s->dir_col[d] < 0) h.general = 1;
     h.weights_floats = round_up_i(sw, 4);
     h.n_units = units;

@@ -99,7 +99,34 @@ class TorchModel(ABC, nn.Module):
         return u
 
 
-_ACT_NAMES = {'tanh': 'tanh', 'sigmoid': 'sigmoid'}          # activations the fused kernel covers
+# activations the fused kernel covers: type name (lower case) -> (kernel name, closed form).  A module is accepted
+# only if it also BEHAVES like the closed form on a probe (nn.Softplus(beta=2), nn.GELU('tanh'), a user class
+# that happens to be called Sin … go to the autograd path instead).
+_ACT_NAMES = {
+    'tanh': ('tanh', torch.tanh),
+    'sigmoid': ('sigmoid', torch.sigmoid),
+    'sin': ('sin', torch.sin),
+    'softplus': ('softplus', nn.functional.softplus),
+    'silu': ('silu', nn.functional.silu),
+    'swish': ('silu', nn.functional.silu),
+    'gelu': ('gelu', nn.functional.gelu),
+}
+
+
+def fused_activation_name(module):
+    """ Kernel activation name of an activation module, or None if the fused kernel does not cover it. """
+    entry = _ACT_NAMES.get(type(module).__name__.lower())
+    if entry is None:
+        return None
+    probe = torch.linspace(-4.0, 4.0, 17, dtype=torch.float64).view(-1, 1)
+    try:
+        with torch.no_grad():
+            got = module(probe)
+    except Exception:                                    # pragma: no cover
+        return None
+    if got.shape != probe.shape or not torch.allclose(got, entry[1](probe), rtol=1e-9, atol=1e-12):
+        return None
+    return entry[0]
 
 
 class Sin(nn.Module):
@@ -186,10 +213,9 @@ class DenseBlock(nn.Module):
                 lin, act = ops[i], 'none'
                 i += 1
                 if i < len(kinds) and kinds[i] == 'a':
-                    name = type(ops[i]).__name__.lower()
-                    if name not in _ACT_NAMES:
+                    act = fused_activation_name(ops[i])
+                    if act is None:
                         return None
-                    act = _ACT_NAMES[name]
                     i += 1
                 chain.append([lin, act, None])
             elif kind in 'R+':

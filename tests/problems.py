@@ -14,6 +14,11 @@ import torch
 PI = math.pi
 
 
+class Sin(torch.nn.Module):                          # the reference takes activation callables (model_torch.py:150-151)
+    def forward(self, x):
+        return torch.sin(x)
+
+
 def _poisson2d(f, x, y, D, V):                       # README.md:36-37
     return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
 
@@ -77,6 +82,10 @@ def _heat1d(f, x, t, D, V):
     return D(D(f, x), x) - D(f, t)
 
 
+def _wave1d(f, x, t, D, V):
+    return D(D(f, t), t) - 0.25 * D(D(f, x), x)
+
+
 def _ic_sin(x):
     return torch.sin(PI * x)
 
@@ -135,14 +144,30 @@ PROBLEMS = {
                      ranges=[(0, 1), (0, 1), (0, 1)], log_scale=0.2),
     'nonlinear': dict(equation=_nonlinear, ndims=2, nparams=0, ic=None, bc=None, domain=(0, 1),
                       features=[7, 5, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1), (0, 1)]),
+    # activations outside the tanh / sigmoid family (reference docstring :150-151: callables and nn.* names)
+    'poisson_sin': dict(equation=_poisson2d, ndims=2, nparams=0, ic=None, bc=1, domain=(0, 1),
+                        features=[9, 11, 1], activation=Sin, layout='fafaf', ranges=[(0, 1), (0, 1)]),
+    'heat_softplus': dict(equation=_heat2d, ndims=3, nparams=0, ic=_ic_heat, bc=0, domain=(0, 1),
+                          features=[10, 9, 1], activation='Softplus', layout='fafaf',
+                          ranges=[(0, 1), (0, 1), (0, .5)]),
+    'burgers_silu': dict(equation=_burgers, ndims=2, nparams=0, ic=_ic_burgers, bc=0.5,
+                         domain=[(-1, 2), (0, 3)], features=[8, 9, 1], activation='SiLU', layout='fafaf',
+                         ranges=[(-1, 2), (0, 3)], log_scale=0.3),
+    'wave1d_gelu': dict(equation=_wave1d, ndims=2, nparams=0, ic=_ic_sin, bc=0, domain=(0, 1),
+                        features=[12, 10, 1], activation='GELU', layout='fafaf', ranges=[(0, 1), (0, 1)]),
+    'mixed_acts_skip': dict(equation=_mixed2d, ndims=2, nparams=0, ic=None, bc=0.3, domain=[(0, 2), (-1, 1)],
+                            features=[8, 8, 8, 1], activation=[Sin, 'GELU', 'Tanh'], layout='fa R fa fa+ f',
+                            ranges=[(0, 2), (-1, 1)]),
 }
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
-                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75}
+                'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75,
+                'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
-               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01)}
+               'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01),
+               'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01)}
 
 
 def make_points(name, batch, seed):
@@ -157,11 +182,17 @@ def layer_plan(name):
     """ (activation per dense layer, skip source per dense layer) parsed from the layout string. """
     cfg = PROBLEMS[name]
     acts, skips, stack = [], [], []
-    for letter in cfg['layout'].replace(' ', ''):
+    layout = cfg['layout'].replace(' ', '')
+    spec = cfg['activation']
+    spec = list(spec) if isinstance(spec, (list, tuple)) else [spec] * layout.count('a')
+    names = [(a if isinstance(a, str) else a.__name__).lower() for a in spec]
+    i_a = 0
+    for letter in layout:
         if letter == 'f':
             acts.append('none'); skips.append(None)
         elif letter == 'a':
-            acts[-1] = cfg['activation'].lower()
+            acts[-1] = names[i_a]
+            i_a += 1
         elif letter == 'R':
             stack.append(len(acts) - 1)
         elif letter == '+':

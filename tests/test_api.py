@@ -94,6 +94,15 @@ def test_lowering_decisions():
     assert s._traced is None and 'dense chain' in s._lower_error
     s.fit(niters=2, batch_size=8)
     s = Solver(pde, ndims=2, layout='fa fa f', features=[4, 4, 1], activation='Sin', device='cpu')
+    assert s._traced is not None and [c[1] for c in s._chain] == ['sin', 'sin', 'none']
+    s = Solver(pde, ndims=2, layout='fa fa fa f', features=[4, 4, 4, 1], activation=['Softplus', torch.nn.SiLU, 'GELU'],
+               device='cpu')
+    assert [c[1] for c in s._chain] == ['softplus', 'silu', 'gelu', 'none']
+    s = Solver(pde, ndims=2, layout='fa fa f', features=[4, 4, 1], activation='ELU', device='cpu')
+    assert s._traced is None                                      # not among the fused activations
+    s = Solver(pde, ndims=2, layout='fa f', features=[4, 1], activation=torch.nn.Softplus(beta=2.0), device='cpu')
+    assert s._traced is None                                      # right name, different function
+    s = Solver(pde, ndims=2, layout='fa f', features=[4, 1], activation=torch.nn.GELU(approximate='tanh'), device='cpu')
     assert s._traced is None
 
     class MyModel(ConvBlockModel):

@@ -23,7 +23,8 @@ def test_device_math_matches_reference(name):
     assert rel_l2(u, g['u']) <= 1e-5
 
 
-@pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var'])
+@pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var', 'poisson_sin', 'heat_softplus', 'burgers_silu',
+                                  'wave1d_gelu', 'mixed_acts_skip'])
 def test_device_math_vs_fp64(name):
     g = load_golden(name)
     spec = E.spec_for(name)

@@ -37,7 +37,8 @@ def test_step_matches_reference_golden(name):
     assert rel_l2(u, g['u']) <= 1e-5
 
 
-@pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var', 'wave3d'])
+@pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var', 'wave3d', 'poisson_sin', 'burgers_silu',
+                                  'wave1d_gelu', 'heat_softplus'])
 def test_gradient_error_vs_fp64_no_worse_than_reference(name):
     g = load_golden(name)
     solver = make_solver(name, g['params'])

@@ -61,3 +61,60 @@ def test_numpy_sampler_host_api():
     assert s3.sample(10).shape == (10, 4)
     assert s3.device_columns() == [(0, 0.0, 1.0), (0, 0.0, 1.0), (1, 1.0, 2.0), (2, 3.0, 0.0)]
     assert NumpySampler('exponential', scale=2.0).device_columns() is None
+
+
+def test_sampler_algebra_on_the_host():
+    """ The rest of the sampler algebra the reference re-exports (pydens/__init__.py:5): weights, mixtures,
+    arithmetic, apply, truncate, scipy / histogram samplers. """
+    from pydens_b200 import ScipySampler, HistoSampler
+    u = NumpySampler('u', seed=3)
+    # affine transforms of uniform / normal / constant columns still run in-kernel
+    s = 2.0 * NumpySampler('u', low=1, high=2) + 1.0
+    assert s.device_columns() == [(0, 3.0, 5.0)]
+    x = s.sample(2000)
+    assert x.shape == (2000, 1) and x.min() >= 3.0 and x.max() <= 5.0
+    s = (1.0 - NumpySampler('n', loc=2.0, scale=0.5, seed=1)) / 2.0
+    assert s.device_columns() == [(1, -0.5, 0.25)]
+    x = s.sample(50000)
+    assert abs(x.mean() + 0.5) < 0.01 and abs(x.std() - 0.25) < 0.01
+    assert (-u).device_columns() == [(0, 0.0, -1.0)] and (ConstantSampler(2.0) * 3).device_columns() == [(2, 6.0, 0.0)]
+    assert (np.array([1.0, 2.0]) * NumpySampler('u', dim=2)).device_columns() is None     # per-column factors: host
+    x = (np.array([1.0, 2.0]) * NumpySampler('u', dim=2, seed=0) + NumpySampler('u', dim=2, seed=1)).sample(100)
+    assert x.shape == (100, 2) and x[:, 1].max() <= 3.0
+    # mixture with weights: 1/4 of the points from [0, 1), 3/4 from [10, 11)
+    mix = 0.25 & NumpySampler('u', seed=5) | 0.75 & NumpySampler('u', low=10, high=11, seed=6)
+    x = mix.sample(40000)
+    assert x.shape == (40000, 1) and mix.device_columns() is None
+    assert abs((x < 5).mean() - 0.25) < 0.01
+    assert abs((x[:20000] < 5).mean() - 0.25) < 0.02      # shuffled, not blockwise
+    tri = (NumpySampler('u', seed=1) | NumpySampler('u', low=2, high=3, seed=2)) | NumpySampler('u', low=4, high=5, seed=3)
+    x = tri.sample(30000)
+    assert abs((x < 1.5).mean() - 1 / 3) < 0.015 and abs((x > 3.5).mean() - 1 / 3) < 0.015
+    # apply / truncate
+    disc = NumpySampler('u', low=-1, high=1, dim=2, seed=7).truncate(high=1.0, expr=lambda p: (p ** 2).sum(axis=1), prob=0.7)
+    x = disc.sample(5000)
+    assert x.shape == (5000, 2) and ((x ** 2).sum(axis=1) <= 1.0).all()
+    x = NumpySampler('n', dim=2, seed=8).truncate(low=[-1, 0], high=[1, 2]).sample(1000)
+    assert x.shape == (1000, 2) and x[:, 0].min() >= -1 and x[:, 1].min() >= 0 and x[:, 1].max() <= 2
+    import pytest
+    with pytest.raises(ValueError):
+        NumpySampler('u', seed=1).truncate(low=2.0, max_iters=3).sample(10)
+    assert NumpySampler('u', seed=1).truncate(low=2.0, max_iters=2, sample_anyway=True).sample(10).shape == (10, 1)
+    polar = NumpySampler('u', dim=2, seed=9).apply(lambda p: np.stack([p[:, 0] * np.cos(p[:, 1]), p[:, 0] * np.sin(p[:, 1]), p[:, 0]], axis=1))
+    assert polar.dim == 3 and polar.sample(64).shape == (64, 3)
+    # scipy / histogram samplers
+    x = ScipySampler('beta', a=2.0, b=5.0, seed=1).sample(20000)
+    assert x.shape == (20000, 1) and abs(x.mean() - 2 / 7) < 0.01
+    h = HistoSampler(edges=[np.linspace(0, 1, 5), np.linspace(0, 2, 3)], seed=2)
+    h.update(np.array([[0.1, 0.5], [0.1, 0.6], [0.9, 1.5]]))
+    x = h.sample(9000)
+    assert x.shape == (9000, 2) and abs((x[:, 0] < 0.25).mean() - 2 / 3) < 0.02
+    assert ((x[:, 0] < 0.25) == (x[:, 1] < 1.0)).all()
+    h1 = HistoSampler(histo=np.histogram(np.random.RandomState(0).normal(size=5000), bins=30), seed=3)
+    assert abs(h1.sample(20000).mean()) < 0.05
+    # anything with .sample(size) feeds Solver.fit (CPU: autograd path; on the GPU through pinned staging)
+    import torch
+    from pydens_b200 import Solver, D
+    s = Solver(lambda f, x, e: D(f, x) - e * torch.cos(e * x), ndims=1, nparams=1, initial_condition=1.0, device='cpu')
+    s.fit(niters=2, batch_size=16, sampler=NumpySampler('u') & (0.5 & NumpySampler('u', low=1, high=2) | NumpySampler('n', loc=4, scale=.1)))
+    assert len(s.losses) == 2
