@@ -103,10 +103,12 @@ class FusedEngine:
         skips = [c[2] for c in chain]
         has_bc = model.boundary_condition is not None
         has_ic = model.raw_initial_condition is not None
-        self.spec = _native.build_spec(widths, acts, model.ndims, model.nparams, has_bc,
-                                       model.boundary_condition if has_bc else 0.0, has_ic, model.domain, traced,
-                                       var_offsets=var_offsets, w_off=w_off, b_off=b_off,
-                                       log_scale_off=log_scale_off, n_params=self.n_params, skips=skips)
+        self._spec_args = (widths, acts, model.ndims, model.nparams, has_bc,
+                           model.boundary_condition if has_bc else 0.0, has_ic, model.domain)
+        self._spec_kwargs = dict(var_offsets=var_offsets, w_off=w_off, b_off=b_off, log_scale_off=log_scale_off,
+                                 n_params=self.n_params, skips=skips)
+        self.spec = _native.build_spec(*self._spec_args, traced, **self._spec_kwargs)
+        self._constraint_plans = {}                       # num -> fused constraint launch (see _constraint_plan)
         plan = C.c_void_p()
         _native.check(self.lib.pinn_plan_create(C.byref(self.spec), self.device.index, C.byref(plan)))
         self.plan = plan
@@ -156,11 +158,45 @@ class FusedEngine:
             if getattr(self, 'comm', None):
                 self.lib.pinn_comm_destroy(self.comm)
                 self.comm = None
+            for entry in getattr(self, '_constraint_plans', {}).values():
+                if entry is not None and entry.get('plan'):
+                    self.lib.pinn_plan_destroy(entry['plan'])
+                    entry['plan'] = None
             if getattr(self, 'plan', None):
                 self.lib.pinn_plan_destroy(self.plan)
                 self.plan = None
         except Exception:                                  # pragma: no cover
             pass
+
+    def _constraint_plan(self, num):
+        """ Constraint `num` as one more launch of the same kernel family (reference :451-457): a plan whose
+        residual program is the traced constraint (no derivative channels), run on the constraint's own points
+        with 1/n weighting; its [grads | loss] buffer is then added to the step's.  None -> autograd adds it. """
+        if num not in self._constraint_plans:
+            entry = None
+            lowered = self.solver._lower_constraint(num)
+            if lowered is not None:
+                traced, pts = lowered
+                spec = _native.build_spec(*self._spec_args, traced, **self._spec_kwargs)
+                plan = C.c_void_p()
+                rc = self.lib.pinn_plan_create(C.byref(spec), self.device.index, C.byref(plan))
+                if rc == 0:
+                    ws = torch.zeros(self.lib.pinn_workspace_bytes(plan, 1), dtype=torch.uint8, device=self.device)
+                    entry = dict(plan=plan, spec=spec, points=pts.to(self.device).contiguous(), n=int(pts.shape[0]),
+                                 out=torch.zeros(self.n_params + 4, dtype=torch.float32, device=self.device),
+                                 workspace=ws)
+                elif rc != _native.E_UNSUPPORTED:
+                    _native.check(rc)
+            self._constraint_plans[num] = entry
+        return self._constraint_plans[num]
+
+    def _constraint_step(self, entry):
+        _native.check(self.lib.pinn_step(
+            entry['plan'], C.c_void_p(self.flat.data_ptr()), C.c_void_p(entry['points'].data_ptr()), None,
+            C.c_uint64(self.seed), None, C.c_uint64(0), C.c_uint64(0), C.c_int64(entry['n']),
+            C.c_float(1.0 / entry['n']), C.c_void_p(entry['out'].data_ptr()), None,
+            C.c_void_p(entry['workspace'].data_ptr()), C.c_size_t(entry['workspace'].numel()), self._stream()))
+        self.out.add_(entry['out'])                       # [grads | loss] += the constraint's
 
     def release(self):
         """ Give every parameter its own storage back (the autograd path is taking over). """
@@ -224,6 +260,8 @@ class FusedEngine:
         solver._make_optimizer(optimizer, lr, fused_hint=True, **kwargs)
         opt = solver.optimizer
         nums = solver._constraint_numbers(loss_terms)
+        fused_constraints = [e for e in (self._constraint_plan(n) for n in nums) if e is not None]
+        nums = [n for n in nums if self._constraint_plan(n) is None]     # the rest is added by autograd
         dist = _dist()
         world = dist.get_world_size() if dist is not None else 1
         rank = dist.get_rank() if dist is not None else 0
@@ -266,6 +304,8 @@ class FusedEngine:
             self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
             if dist is not None and self.comm is None:
                 dist.all_reduce(self.out)              # no peer-memory path: NCCL sums [grads | loss]
+            for entry in fused_constraints:            # after the all-reduce: every rank adds the same term
+                self._constraint_step(entry)
             if nums:
                 xs = solver._sample_host(sampler if host_sampler is not None else None, batch_size) \
                     if points is None else [points[:, k:k + 1] for k in range(total)]

@@ -94,6 +94,7 @@ class Solver:
 
         self._engine = None
         self._traced = None
+        self._traced_constraints = {}                     # num -> (TracedEquation, points [n, total]) or None
         self._lower_error = None
         self._warned = False
         if backend != 'torch':
@@ -141,6 +142,37 @@ class Solver:
         except tracer.NotLowerable as exc:
             self._traced = None
             self._lower_error = str(exc)
+
+    def _tracing_run(self, fn, *args):
+        def call():
+            token = _tracing.set(True)
+            try:
+                return fn(*args)
+            finally:
+                _tracing.reset(token)
+        return self.ctx.run(call)
+
+    def _lower_constraint(self, num):
+        """ (traced constraint, its points as a [n, total] fp32 tensor) if constraint `num` can run as a fused
+        launch — one model evaluation at fixed points, combined pointwise — else None (autograd adds it). """
+        if num not in self._traced_constraints:
+            lowered = None
+            if self._traced is not None and os.environ.get('PYDENS_B200_FUSED_CONSTRAINTS') != '0':
+                model = self.model
+                try:
+                    traced, args = tracer.trace_constraint(self.constraints[num], model.total,
+                                                           initial_condition=model.raw_initial_condition,
+                                                           ndims_spatial=model.ndims_spatial, run=self._tracing_run)
+                    pts = self.reshape_and_concat(args).detach().to(torch.float32)
+                    if pts.dim() != 2 or pts.shape[1] != model.total or pts.shape[0] < 1:
+                        raise tracer.NotLowerable('constraint points do not have %d columns' % model.total)
+                    if not set(traced.var_names) <= set(self._traced.var_names):
+                        raise tracer.NotLowerable('constraint introduces new variables')
+                    lowered = (traced, pts.contiguous())
+                except (tracer.NotLowerable, TypeError, ValueError, RuntimeError, IndexError):
+                    lowered = None
+            self._traced_constraints[num] = lowered
+        return self._traced_constraints[num]
 
     def _get_engine(self):
         if self._engine is None:

@@ -725,3 +725,32 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
         T.ic_prog = lower(jet, {}, var_index, base)
         T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
     return T
+
+
+def trace_constraint(constraint, total, initial_condition=None, ndims_spatial=0, run=None):
+    """ Trace a constraint `constraint(u, *xs)` (reference model_torch.py:451-457: `u` is a callable that
+    evaluates the model at user points, the value is driven to zero by MSE) into the same program form as an
+    equation.  Lowerable when the constraint evaluates the model ONCE, at concrete points, and combines that
+    value pointwise with constants / variables: `lambda u, t: u(torch.tensor([0.5]))`, `… - 2.0`, `… ** 2`.
+
+    Returns (TracedEquation with no derivative directions, the tuple of point arguments of the one call).
+    """
+    calls = []
+
+    def u_at(*pts):
+        if any(isinstance(p, Sym) for p in pts):
+            raise NotLowerable('constraint evaluates the model at the batch points')
+        if calls:
+            raise NotLowerable('constraint evaluates the model more than once')
+        calls.append(pts)
+        return Sym(uleaf())
+
+    traced = trace(lambda _u, *xs: constraint(u_at, *xs), total, None, initial_condition=initial_condition,
+                   ndims_spatial=ndims_spatial, run=run)
+    if not calls:
+        raise NotLowerable('constraint does not evaluate the model')
+    if traced.nf:
+        raise NotLowerable('derivatives inside a constraint')
+    if leaves(traced.residual, ('coord',)):
+        raise NotLowerable('constraint depends on the batch points')
+    return traced, calls[0]

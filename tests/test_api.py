@@ -120,3 +120,23 @@ def test_sampler_and_domain_handling():
         Solver(pde, ndims=2, domain=3, device='cpu')
     s2 = Solver(pde, ndims=2, domain=[(-1, 1), (0, 2)], boundary_condition=0.5, device='cpu')
     assert np.allclose(s2.predict(-1.0, 1.0), 0.5)
+
+
+def test_constraints_lower_to_fused_launches_when_pointwise():
+    def odevar(u, t):
+        return D(u, t) - 2 * np.pi * torch.cos(2 * np.pi * t)
+
+    def initial(*args):
+        return V('init', data=torch.Tensor([3.0]))
+    s = Solver(odevar, ndims=1, initial_condition=initial, device='cpu',
+               constraints=[lambda u, t: u(torch.tensor([0.5])),                 # README.md:118
+                            lambda u, t: u(np.array([0.25, 0.75])) ** 2 - 1.0,
+                            lambda u, t: u(0.1) - u(0.9),                          # two evaluations: autograd adds it
+                            lambda u, t: (u(0.5) * t).mean()])                     # uses the batch points
+    tr, pts = s._lower_constraint(0)
+    assert tr.channels == 1 and tr.var_names == ['init'] and pts.shape == (1, 1) and float(pts[0, 0]) == 0.5
+    tr, pts = s._lower_constraint(1)
+    assert pts.shape == (2, 1) and len(tr.eq_prog) >= 2
+    assert s._lower_constraint(2) is None and s._lower_constraint(3) is None
+    s.fit(niters=2, batch_size=8, loss_terms=['equation', 'constraint_0', 'constraint_2'])   # CPU: autograd path
+    assert len(s.losses) == 2

@@ -58,3 +58,45 @@ def test_ragged_and_single_point():
         l, r, gr = prob.loss_and_grads(pts)
         assert abs(loss - l) <= 1e-5 * abs(l)
         assert rel_l2(grads, gr.numpy()) <= 1e-4
+
+
+def test_traced_constraint_runs_as_a_plan_without_derivative_channels():
+    """ reference model_torch.py:451-457: a constraint evaluates the model at user points and is driven to zero
+    by MSE.  Lowered form: the same kernel with the constraint as residual program, C = 1 channel. """
+    from pydens_b200 import tracer as T, _native as N
+    import oracle.autograd_port as ap
+    name = 'heat1d_icvar'                                # variables in the equation AND in the initial condition
+    cfg = P.PROBLEMS[name]
+    g = load_golden(name)
+    main, main_tr = E.spec_for(name), E.traced_problem(name)
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    xs0, ts0 = torch.tensor([0.25, 0.5, 0.8]), torch.tensor([0.3, 0.6, 0.05])
+
+    def constraint(u, x, t, V=sym_V):
+        return u(xs0, ts0) ** 2 - 0.3 * V('shift', 0.2)
+    tr, args = T.trace_constraint(constraint, 2, initial_condition=P.make_ic(name, sym_V), ndims_spatial=1)
+    assert tr.nf == 0 and tr.channels == 1 and len(args) == 2 and tr.var_names == ['amp', 'shift']
+    var_offsets = {n: main.var_off[i] for i, n in enumerate(main_tr.var_names)}
+    acts, skips = P.layer_plan(name)
+    spec = N.build_spec([2] + list(cfg['features']), acts, 2, 0, True, cfg['bc'], True, [(0, 1), (0, 1)], tr,
+                        var_offsets=var_offsets, w_off=list(main.w_off[:3]), b_off=list(main.b_off[:3]),
+                        log_scale_off=main.log_scale_off, n_params=main.n_params, skips=skips)
+    pts = torch.stack([xs0, ts0], dim=1).numpy()
+    loss, residual, grads = E.emul_step(spec, g['params'], pts)
+
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    prob.equation = lambda u, x, t, D, V: u ** 2 - 0.3 * V('shift')
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert rel_l2(residual, ref_res) <= 1e-5
+    assert rel_l2(grads[:ref_grads.numel()], ref_grads.numpy()) <= 1e-5
+
+    # what cannot be lowered says so
+    with pytest.raises(T.NotLowerable):
+        T.trace_constraint(lambda u, x, t: u(x, t), 2)                          # model at the batch points
+    with pytest.raises(T.NotLowerable):
+        T.trace_constraint(lambda u, x, t: u(0.1, 0.2) - u(0.3, 0.4), 2)        # two evaluations
+    with pytest.raises(T.NotLowerable):
+        T.trace_constraint(lambda u, x, t: u(0.1, 0.2) * x, 2)                  # mixes in the batch points
+    with pytest.raises(T.NotLowerable):
+        T.trace_constraint(lambda u, x, t: T.sym_D(u(0.1, 0.2) * x, x), 2)

@@ -96,6 +96,44 @@ def test_variable_constraint_hybrid():
     assert len(solver.losses) == 300 and np.isfinite(solver.losses).all()
 
 
+def test_fused_constraint_matches_autograd_constraint(monkeypatch):
+    """ README.md:112-126 flow: V in the initial condition + a constraint at t = 0.5.  The constraint runs as one
+    more fused launch (CUDA-graph capturable); the autograd-added constraint is the yardstick. """
+    def odevar(u, t):
+        return D(u, t) - 2 * np.pi * torch.cos(2 * np.pi * t)
+
+    def initial(*args):
+        return V('init', data=torch.Tensor([3.0]))
+
+    def make():
+        torch.manual_seed(0)
+        return Solver(odevar, ndims=1, initial_condition=initial, layout='fafaf', features=[12, 10, 1], activation='Tanh',
+                      constraints=lambda u, t: u(torch.tensor([0.5])) - 0.25)
+    rng = np.random.RandomState(5)
+    batches = [rng.uniform(size=(150, 1)).astype(np.float32) for _ in range(40)]
+    fused = make()
+    fused.fit(niters=40, batch_size=150, lr=0.05, sampler=Replay(batches), loss_terms=['equation', 'constraint_0'])
+    assert fused._engine is not None and fused._engine._constraint_plans[0] is not None
+    monkeypatch.setenv('PYDENS_B200_FUSED_CONSTRAINTS', '0')
+    hybrid = make()
+    hybrid.fit(niters=40, batch_size=150, lr=0.05, sampler=Replay(batches), loss_terms=['equation', 'constraint_0'])
+    assert hybrid._engine._constraint_plans[0] is None
+    a, b = np.asarray(fused.losses, dtype=np.float64), np.asarray(hybrid.losses, dtype=np.float64)
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 2e-3
+    assert abs(float(fused.model.init.detach()) - float(hybrid.model.init.detach())) <= 1e-4
+    assert float(fused.model.init.detach()) != 3.0
+    monkeypatch.delenv('PYDENS_B200_FUSED_CONSTRAINTS')
+    # in-kernel sampling + graph replay, then the README's second stage: only the variable trains
+    solver = make()
+    solver.fit(niters=200, batch_size=150, lr=0.05, loss_terms=['equation', 'constraint_0'])
+    solver.model.freeze_layers(['fc1', 'fc2', 'fc3'], ['log_scale'])
+    w0 = solver.model.conv_block.linears[0].weight.detach().clone()
+    solver.fit(niters=100, batch_size=150, lr=0.05, loss_terms=['equation', 'constraint_0'])
+    assert torch.equal(w0, solver.model.conv_block.linears[0].weight.detach())
+    assert np.isfinite(solver.losses).all() and np.mean(solver.losses[-20:]) < np.mean(solver.losses[:20])
+    assert abs(float(solver.predict(0.5)) - 0.25) < 0.2          # the constraint pulls u(0.5) to 0.25
+
+
 def test_autograd_path_on_gpu_matches_fused_step():
     """ backend='torch' (device-aware restatement of the reference loop) and the fused kernel agree. """
     g = load_golden('heat_param')
