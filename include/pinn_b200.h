@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   7
+#define PINN_ABI_VERSION   8
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -100,10 +100,20 @@ typedef struct PinnInstr {
 #define PINN_COL_UNIFORM    0   /* a + (b - a) * U[0,1)   */
 #define PINN_COL_NORMAL     1   /* a + b * N(0,1)          */
 #define PINN_COL_CONST      2   /* a                       */
+#define PINN_COL_MIXTURE    3   /* one of n_comp simple columns, drawn per point (batchflow `s1 | s2`) */
+#define PINN_MAX_MIX        4
 
+/* A mixture column picks component i with probability cum_w[i] - cum_w[i-1] (cum_w[n_comp-1] == 1) and then
+ * samples (comp_kind[i], comp_a[i], comp_b[i]) like a simple column.  Columns that carry the same `group`
+ * share the draw of the component — `(a1 & a2) | (b1 & b2)` picks the whole row from one side. */
 typedef struct PinnColumn {
     int32_t kind;
     float   a, b;
+    int32_t group;                       /* 0 .. PINN_MAX_DIMS-1 (mixture columns only)                 */
+    int32_t n_comp;                      /* 2 .. PINN_MAX_MIX                                           */
+    float   cum_w[PINN_MAX_MIX];
+    int32_t comp_kind[PINN_MAX_MIX];     /* PINN_COL_UNIFORM / NORMAL / CONST                           */
+    float   comp_a[PINN_MAX_MIX], comp_b[PINN_MAX_MIX];
 } PinnColumn;
 
 /*

@@ -35,8 +35,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def sample(cols, total, seed, step, point_offset, n):
-    """ cols: [(kind, a, b)] per column (kind 0 uniform [a,b), 1 normal(a, b), 2 const a) or None for
-    the default U[0,1).  Returns float32 [n, total] — bit-exact with pinn_sample for uniform / const
+    """ cols: [(kind, a, b)] per column (kind 0 uniform [a,b), 1 normal(a, b), 2 const a) — or
+    ('mix', group key, [(weight, kind, a, b), ...]) for a mixture column — or None for the default U[0,1).  Returns float32 [n, total] — bit-exact with pinn_sample for uniform / const
     columns (normal columns go through libm log/cos and are compared with a tolerance). """
     if cols is None:
         cols = [(0, 0.0, 1.0)] * total
@@ -55,20 +55,38 @@ def sample(cols, total, seed, step, point_offset, n):
 
     out = np.zeros((n, total), dtype=np.float32)
     scale = np.float32(2.0 ** -24)
-    for k, (kind, a, b) in enumerate(cols):
+
+    def simple(k, kind, a, b):
         a32, b32 = np.float32(a), np.float32(b)
         if kind == 2:
-            out[:, k] = a32
-        elif kind == 0:
+            return np.full(n, a32, dtype=np.float32)
+        if kind == 0:
             w = block(0)[k] if k < 4 else block(1)[k - 4]
             u = (w >> np.uint32(8)).astype(np.float32) * scale
             # fmaf(b - a, u, a): one rounding — emulate in float64 (exact product of two fp32 fits)
-            out[:, k] = ((np.float64(b32 - a32)) * u.astype(np.float64) + np.float64(a32)).astype(np.float32)
+            return ((np.float64(b32 - a32)) * u.astype(np.float64) + np.float64(a32)).astype(np.float32)
+        w = block(2 + k)
+        u1 = ((w[0] >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * scale
+        u2 = (w[1] >> np.uint32(8)).astype(np.float32) * scale
+        rad = np.sqrt(np.float32(-2.0) * np.log(u1))
+        z = rad * np.cos(np.float32(6.283185307179586) * u2)
+        return (np.float64(b32) * z.astype(np.float64) + np.float64(a32)).astype(np.float32)
+
+    groups = {}
+    for k, col in enumerate(cols):
+        if col[0] == 'mix':                        # ('mix', group key, [(weight, kind, a, b), ...])
+            _, key, comps = col
+            g = groups.setdefault(key, len(groups))
+            u = (block(10 + g)[0] >> np.uint32(8)).astype(np.float32) * scale
+            total_w, acc, cum = float(sum(c[0] for c in comps)), 0.0, []
+            for j, c in enumerate(comps):
+                acc += float(c[0])
+                cum.append(np.float32(1.0 if j == len(comps) - 1 else acc / total_w))
+            idx = np.zeros(n, dtype=np.int64)
+            for c in range(len(comps) - 1):
+                idx += (u >= cum[c]).astype(np.int64)
+            vals = np.stack([simple(k, kind, a, b) for _, kind, a, b in comps], axis=0)
+            out[:, k] = vals[idx, np.arange(n)]
         else:
-            w = block(2 + k)
-            u1 = ((w[0] >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * scale
-            u2 = (w[1] >> np.uint32(8)).astype(np.float32) * scale
-            rad = np.sqrt(np.float32(-2.0) * np.log(u1))
-            z = rad * np.cos(np.float32(6.283185307179586) * u2)
-            out[:, k] = (np.float64(b32) * z.astype(np.float64) + np.float64(a32)).astype(np.float32)
+            out[:, k] = simple(k, *col)
     return out

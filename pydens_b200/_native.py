@@ -6,11 +6,12 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
-COL_UNIFORM, COL_NORMAL, COL_CONST = 0, 1, 2
+COL_UNIFORM, COL_NORMAL, COL_CONST, COL_MIXTURE = 0, 1, 2, 3
+MAX_MIX = 4
 
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN, E_WORKSPACE = -1, -2, -3, -4, -5
 
@@ -20,7 +21,9 @@ class PinnInstr(C.Structure):
 
 
 class PinnColumn(C.Structure):
-    _fields_ = [('kind', C.c_int32), ('a', C.c_float), ('b', C.c_float)]
+    _fields_ = [('kind', C.c_int32), ('a', C.c_float), ('b', C.c_float),
+                ('group', C.c_int32), ('n_comp', C.c_int32), ('cum_w', C.c_float * MAX_MIX),
+                ('comp_kind', C.c_int32 * MAX_MIX), ('comp_a', C.c_float * MAX_MIX), ('comp_b', C.c_float * MAX_MIX)]
 
 
 class PinnSpec(C.Structure):
@@ -126,15 +129,28 @@ def check(rc):
 
 
 def make_columns(cols, total):
-    """ cols: list of (kind, a, b) per point column -> ctypes array, or None for the default U[0,1). """
+    """ cols: per point column either (kind, a, b) or ('mix', group_key, [(weight, kind, a, b), ...]) — columns
+    with the same group_key share the component draw — -> ctypes array, or None for the default U[0,1). """
     if cols is None:
         return None
     arr = (PinnColumn * MAX_DIMS)()
+    groups = {}
     for i in range(MAX_DIMS):
-        if i < total:
-            arr[i].kind, arr[i].a, arr[i].b = cols[i]
+        col = cols[i] if i < total else (COL_UNIFORM, 0.0, 1.0)
+        if col[0] == 'mix':
+            _, key, comps = col
+            if not 2 <= len(comps) <= MAX_MIX:
+                raise ValueError('a mixture column takes 2..%d components' % MAX_MIX)
+            arr[i].kind = COL_MIXTURE
+            arr[i].group = groups.setdefault(key, len(groups))
+            arr[i].n_comp = len(comps)
+            total_w, acc = float(sum(c[0] for c in comps)), 0.0
+            for j, (w, kind, a, b) in enumerate(comps):
+                acc += float(w)
+                arr[i].cum_w[j] = 1.0 if j == len(comps) - 1 else acc / total_w
+                arr[i].comp_kind[j], arr[i].comp_a[j], arr[i].comp_b[j] = int(kind), float(a), float(b)
         else:
-            arr[i].kind, arr[i].a, arr[i].b = COL_UNIFORM, 0.0, 1.0
+            arr[i].kind, arr[i].a, arr[i].b = col
     return arr
 
 

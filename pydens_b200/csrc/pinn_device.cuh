@@ -131,14 +131,15 @@ PINN_HD uint32_t philox_word(const Philox4& p, int i) {
 
 // Coordinate k of the point with global index `gidx` at step `step`.
 // Counter = (gidx lo, gidx hi, step lo, (step hi & 0xffff) << 16 | block); key = seed.
-// block 0/1 serve uniform columns 0-3 / 4-7 (one word each); block 2+k serves normal column k.
-PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_t step, uint64_t seed,
+// block 0/1 serve uniform columns 0-3 / 4-7 (one word each); block 2+k serves normal column k;
+// block 10+g, word 0 picks the component of mixture group g.
+PINN_HD float sample_simple(int kind, float a, float b, int k, uint64_t gidx, uint64_t step, uint64_t seed,
                             const Philox4& blk0, const Philox4& blk1) {
-    if (col.kind == PINN_COL_CONST) return col.a;
-    if (col.kind == PINN_COL_UNIFORM) {
+    if (kind == PINN_COL_CONST) return a;
+    if (kind == PINN_COL_UNIFORM) {
         uint32_t w = (k < 4) ? philox_word(blk0, k) : philox_word(blk1, k - 4);
         float u = u01_from_bits(w);
-        return fmaf(col.b - col.a, u, col.a);
+        return fmaf(b - a, u, a);
     }
     // normal: Box-Muller on a dedicated Philox block
     uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16) | (uint32_t)(2 + k);
@@ -148,7 +149,20 @@ PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_
     float u2 = u01_from_bits(p.y);
     float rad = sqrtf(-2.0f * logf(u1));
     float z = rad * cosf(6.283185307179586f * u2);
-    return fmaf(col.b, z, col.a);
+    return fmaf(b, z, a);
+}
+
+PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_t step, uint64_t seed,
+                            const Philox4& blk0, const Philox4& blk1) {
+    if (col.kind != PINN_COL_MIXTURE) return sample_simple(col.kind, col.a, col.b, k, gidx, step, seed, blk0, blk1);
+    uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16) | (uint32_t)(10 + col.group);
+    Philox4 p = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u = u01_from_bits(p.x);
+    int i = 0;
+#pragma unroll
+    for (int c = 0; c < PINN_MAX_MIX - 1; ++c) i += (c < col.n_comp - 1 && u >= col.cum_w[c]) ? 1 : 0;
+    return sample_simple(col.comp_kind[i], col.comp_a[i], col.comp_b[i], k, gidx, step, seed, blk0, blk1);
 }
 
 // ----------------------------------------------------------------------------------------------

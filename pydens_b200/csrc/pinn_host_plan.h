@@ -94,6 +94,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
         h.lo[i] = s->dom_lo[i]; h.hi[i] = s->dom_hi[i];
         float w = s->dom_hi[i] - s->dom_lo[i];
         h.inv_w2[i] = (i < s->ndims && w != 0.0f) ? 1.0f / (w * w) : 0.0f;
+        memset(&h.cols[i], 0, sizeof(PinnColumn));
         h.cols[i].kind = PINN_COL_UNIFORM; h.cols[i].a = 0.0f; h.cols[i].b = 1.0f;
     }
     memcpy(h.eq_out, s->eq_out, sizeof(h.eq_out));

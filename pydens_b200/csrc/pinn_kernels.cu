@@ -139,6 +139,16 @@ struct PinnPlan {
 extern "C" const char* pinn_last_error(void) { return g_err; }
 extern "C" int pinn_abi_version(void) { return PINN_ABI_VERSION; }
 
+// The dynamic shared-memory limit is an attribute of the KERNEL, shared by every plan that uses the same
+// instantiation: raise it to the device maximum once instead of to this plan's size, so that creating a second
+// plan (another Solver, a constraint plan) can never lower it under a plan that is still in use.
+static cudaError_t allow_max_smem(const void* fn, int smem_optin) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
+}
+
 extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     if (!s || !out) return fail(PINN_E_INVALID, "null argument");
     const Variant* var = nullptr;
@@ -213,8 +223,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         if (SL.total_f * 4 > budget) { delete p; return fail(PINN_E_UNSUPPORTED, "network too large: %d B of weights do not fit shared memory", SL.total_f * 4); }
         p->gmem = true; p->threads = nw * 32; p->n_wacc = nwacc; p->smem_bytes = SL.total_f * 4;
     }
-    e = cudaFuncSetAttribute((const void*)(p->gmem ? p->fn_gmem : p->fn_smem),
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
+    e = allow_max_smem((const void*)(p->gmem ? p->fn_gmem : p->fn_smem), p->smem_optin);
     if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", p->smem_bytes, cudaGetErrorString(e)); }
 
     // forward kernel config
@@ -225,8 +234,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         else { p->fwd_gmem = true; SL = smem_layout(h.weights_floats, 0, 0, h.n_params); }
         p->fwd_threads = nw * 32; p->fwd_smem_bytes = SL.total_f * 4;
         if (p->fwd_smem_bytes > p->smem_optin - 64) { delete p; return fail(PINN_E_UNSUPPORTED, "network too large for shared memory"); }
-        e = cudaFuncSetAttribute((const void*)(p->fwd_gmem ? forward_kernel<true> : forward_kernel<false>),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, p->fwd_smem_bytes);
+        e = allow_max_smem((const void*)(p->fwd_gmem ? forward_kernel<true> : forward_kernel<false>), p->smem_optin);
         if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); }
     }
 
@@ -273,9 +281,21 @@ extern "C" int pinn_out_floats(const PinnPlan* p) { return p ? p->h.n_params + 4
 // The sampler columns of a call are written into a by-value copy of the plan (kernel parameter).
 static int resolve_cols(const PinnPlan* p, const PinnColumn* cols, PinnColumn* out) {
     for (int i = 0; i < PINN_MAX_DIMS; ++i) {
+        memset(&out[i], 0, sizeof(PinnColumn));
         if (cols && i < p->h.total) out[i] = cols[i];
         else { out[i].kind = PINN_COL_UNIFORM; out[i].a = 0.0f; out[i].b = 1.0f; }
-        if (out[i].kind < 0 || out[i].kind > PINN_COL_CONST) return fail(PINN_E_INVALID, "column %d kind %d", i, out[i].kind);
+        const PinnColumn& c = out[i];
+        if (c.kind < 0 || c.kind > PINN_COL_MIXTURE) return fail(PINN_E_INVALID, "column %d kind %d", i, c.kind);
+        if (c.kind == PINN_COL_MIXTURE) {
+            if (c.n_comp < 2 || c.n_comp > PINN_MAX_MIX || c.group < 0 || c.group >= PINN_MAX_DIMS)
+                return fail(PINN_E_INVALID, "column %d: mixture of %d components in group %d", i, c.n_comp, c.group);
+            float prev = 0.0f;
+            for (int j = 0; j < c.n_comp; ++j) {
+                if (c.comp_kind[j] < 0 || c.comp_kind[j] > PINN_COL_CONST || !(c.cum_w[j] >= prev) || c.cum_w[j] > 1.0f + 1e-6f)
+                    return fail(PINN_E_INVALID, "column %d: mixture component %d", i, j);
+                prev = c.cum_w[j];
+            }
+        }
     }
     return PINN_OK;
 }

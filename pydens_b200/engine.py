@@ -280,8 +280,11 @@ class FusedEngine:
         if sampler is not None:
             dev_cols = sampler.device_columns() if hasattr(sampler, 'device_columns') else None
             if dev_cols is not None and len(dev_cols) == total and os.environ.get('PYDENS_B200_HOST_SAMPLER') != '1':
-                cols = _native.make_columns(dev_cols, total)
-            else:
+                try:
+                    cols = _native.make_columns(dev_cols, total)
+                except ValueError:                    # more mixture components than the kernel takes
+                    cols = None
+            if cols is None:
                 host_sampler = sampler
         solver.model.train()
 

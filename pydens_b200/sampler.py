@@ -110,6 +110,34 @@ class _Mixture(Sampler):
         self.weight = left.weight + right.weight          # so that (a | b) | c keeps the three weights
         self.state = np.random.RandomState(seed)
 
+    def device_columns(self):
+        """ In-kernel form: per column ('mix', group key, [(weight, kind, a, b), …]); every column of this
+        mixture carries the same key, so one draw per point picks the side for the whole row.  Each side must be
+        made of simple columns or be such a mixture itself (`(a | b) | c`), at most 4 components in all. """
+        sides = []
+        for side in (self.left, self.right):
+            cols = side.device_columns()
+            if cols is None:
+                return None
+            keys = {c[1] for c in cols if c[0] == 'mix'}
+            if keys and (len(keys) > 1 or any(c[0] != 'mix' for c in cols)):
+                return None                               # a side that mixes only some of its columns
+            sides.append((side.weight, cols))
+        out = []
+        for k in range(self.dim):
+            comps = []
+            for weight, cols in sides:
+                col = cols[k]
+                if col[0] == 'mix':
+                    inner = float(sum(c[0] for c in col[2]))
+                    comps += [(weight * c[0] / inner, c[1], c[2], c[3]) for c in col[2]]
+                else:
+                    comps.append((weight, col[0], col[1], col[2]))
+            if len(comps) > 4:
+                return None
+            out.append(('mix', id(self), comps))
+        return out
+
     def sample(self, size):
         n_left = self.state.binomial(size, self.left.weight / (self.left.weight + self.right.weight))
         pts = np.concatenate([np.asarray(self.left.sample(n_left), dtype=np.float64).reshape(n_left, self.dim),
@@ -140,7 +168,7 @@ class _Arith(Sampler):
         if len(samplers) != 1 or not _is_number(self.left if samplers[0] is self.right else self.right):
             return None
         cols = samplers[0].device_columns()
-        if cols is None:
+        if cols is None or any(col[0] == 'mix' for col in cols):
             return None
         c = float(self.left if samplers[0] is self.right else self.right)
         sampler_first = samplers[0] is self.left

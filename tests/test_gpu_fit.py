@@ -134,6 +134,36 @@ def test_fused_constraint_matches_autograd_constraint(monkeypatch):
     assert abs(float(solver.predict(0.5)) - 0.25) < 0.2          # the constraint pulls u(0.5) to 0.25
 
 
+def test_plans_sharing_a_kernel_instantiation_coexist():
+    """ The dynamic shared-memory limit belongs to the kernel, not to the plan: a later, smaller plan of the same
+    instantiation must not lower it under an earlier plan that is still in use. """
+    g = load_golden('poisson2d')
+    big = make_solver('poisson2d', g['params'])
+    ref_loss, ref_grads, _ = big.loss_and_grads(g['points'])
+    ref_u = big.predict(g['points'][:, 0], g['points'][:, 1])
+
+    def pde(f, x, y):
+        return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
+    small = Solver(pde, ndims=2, boundary_condition=1, layout='faf', features=[3, 1], activation='Tanh')
+    small.loss_and_grads(g['points'])
+    small.predict(0.5, 0.5)
+    loss, grads, _ = big.loss_and_grads(g['points'])
+    assert loss == ref_loss and torch.equal(grads, ref_grads)
+    assert np.array_equal(big.predict(g['points'][:, 0], g['points'][:, 1]), ref_u)
+    big.fit(niters=3, batch_size=1000)
+    small.fit(niters=3, batch_size=1000)
+
+
+def test_mixture_sampler_runs_in_kernel():
+    s = Solver(lambda f, x, e: D(f, x) - e * np.pi * torch.cos(e * np.pi * x), ndims=1, nparams=1, initial_condition=1.0)
+    sampler = NumpySampler('u') & (0.5 & NumpySampler('u', low=1, high=2) | NumpySampler('n', loc=4, scale=.1))
+    assert sampler.device_columns() is not None
+    s.fit(niters=80, batch_size=2000, sampler=sampler, lr=0.01)
+    assert len(s.losses) == 80 and np.isfinite(s.losses).all()
+    pts = s._engine.sample(30000, sampler.device_columns(), step=3).cpu().numpy()
+    assert abs((pts[:, 1] < 3).mean() - 1 / 3) < 0.015 and pts[:, 0].min() >= 0 and pts[:, 0].max() < 1
+
+
 def test_autograd_path_on_gpu_matches_fused_step():
     """ backend='torch' (device-aware restatement of the reference loop) and the fused kernel agree. """
     g = load_golden('heat_param')

@@ -85,6 +85,20 @@ def test_sampler_bit_exact_against_oracle():
     dev = eng.sample(4096, ncols, step=2).cpu().numpy()
     ref = ph.sample(ncols, 4, eng.seed, 2, 0, 4096)
     assert np.array_equal(dev[:, 1:3], ref[:, 1:3]) and np.abs(dev - ref).max() <= 4e-6
+    # mixture columns (batchflow `s1 | s2`): the component draw is integer work -> bit-exact
+    mcols = [('mix', 'a', [(1.0, 0, 0.0, 1.0), (3.0, 0, 10.0, 11.0)]), ('mix', 'a', [(1.0, 2, -5.0, 0.0), (3.0, 0, 20.0, 21.0)]),
+             (0, 0.0, 1.0), ('mix', 'b', [(0.2, 0, 0.0, 1.0), (0.3, 0, 2.0, 3.0), (0.5, 0, 4.0, 5.0)])]
+    dev = eng.sample(8192, mcols, step=3, point_offset=2 ** 35).cpu().numpy()
+    assert np.array_equal(dev, ph.sample(mcols, 4, eng.seed, 3, 2 ** 35, 8192))
+    # and the fused step on a mixture sampler == the same step fed those points explicitly
+    from pydens_b200 import _native as N
+    n = 5000
+    eng._step(None, N.make_columns(mcols, 4), n, 1.0 / n, 0, use_counter=False, step_value=4)
+    torch.cuda.synchronize()
+    sampled = eng.out.clone()
+    eng._step(eng.sample(n, mcols, step=4), None, n, 1.0 / n, 0, use_counter=False, step_value=4)
+    torch.cuda.synchronize()
+    assert torch.equal(sampled, eng.out)
 
 
 def test_in_kernel_sampling_equals_explicit_points():

@@ -84,7 +84,7 @@ def test_sampler_algebra_on_the_host():
     # mixture with weights: 1/4 of the points from [0, 1), 3/4 from [10, 11)
     mix = 0.25 & NumpySampler('u', seed=5) | 0.75 & NumpySampler('u', low=10, high=11, seed=6)
     x = mix.sample(40000)
-    assert x.shape == (40000, 1) and mix.device_columns() is None
+    assert x.shape == (40000, 1) and mix.device_columns()[0][0] == 'mix'          # runs in-kernel, too
     assert abs((x < 5).mean() - 0.25) < 0.01
     assert abs((x[:20000] < 5).mean() - 0.25) < 0.02      # shuffled, not blockwise
     tri = (NumpySampler('u', seed=1) | NumpySampler('u', low=2, high=3, seed=2)) | NumpySampler('u', low=4, high=5, seed=3)
@@ -118,3 +118,48 @@ def test_sampler_algebra_on_the_host():
     s = Solver(lambda f, x, e: D(f, x) - e * torch.cos(e * x), ndims=1, nparams=1, initial_condition=1.0, device='cpu')
     s.fit(niters=2, batch_size=16, sampler=NumpySampler('u') & (0.5 & NumpySampler('u', low=1, high=2) | NumpySampler('n', loc=4, scale=.1)))
     assert len(s.losses) == 2
+
+
+def test_mixture_columns_in_kernel_form():
+    """ `s1 | s2` with weights lowers to PINN_COL_MIXTURE columns: the device code (host build) is bit-exact
+    with the numpy restatement, the component frequencies follow the weights, and the columns of one mixture
+    switch together. """
+    key = 'g0'
+    cols = [('mix', key, [(1.0, 0, 0.0, 1.0), (3.0, 0, 10.0, 11.0)]),
+            ('mix', key, [(1.0, 2, -5.0, 0.0), (3.0, 0, 20.0, 21.0)]),
+            (0, 0.0, 1.0),
+            ('mix', 'g1', [(0.2, 0, 0.0, 1.0), (0.3, 0, 2.0, 3.0), (0.5, 0, 4.0, 5.0)])]
+    a = ph.sample(cols, 4, 77, 5, 2 ** 34, 20000)
+    b = E.emul_sample(cols, 4, 77, 5, 2 ** 34, 20000)
+    assert np.array_equal(a, b)
+    left = a[:, 0] < 5
+    assert abs(left.mean() - 0.25) < 0.01
+    assert np.array_equal(left, a[:, 1] == -5.0)                   # same group: the whole row switches side
+    assert abs((a[:, 3] < 1.5).mean() - 0.2) < 0.01 and abs((a[:, 3] > 3.5).mean() - 0.5) < 0.012
+    assert abs(np.corrcoef(left, a[:, 3] > 3.5)[0, 1]) < 0.03     # different groups: independent draws
+    normal_mix = [('mix', 0, [(1.0, 1, -3.0, 0.5), (1.0, 1, 3.0, 0.5)])]
+    x = ph.sample(normal_mix, 1, 1, 0, 0, 50000)[:, 0]
+    y = E.emul_sample(normal_mix, 1, 1, 0, 0, 50000)[:, 0]
+    assert np.abs(x - y).max() <= 4e-6 and abs((x < 0).mean() - 0.5) < 0.01 and abs(np.abs(x).mean() - 3.0) < 0.02
+
+    # the sampler algebra produces that form
+    u = NumpySampler
+    mix = 0.25 & u('u') | 0.75 & u('u', low=10, high=11)
+    dc = mix.device_columns()
+    assert len(dc) == 1 and dc[0][0] == 'mix' and dc[0][2] == [(0.25, 0, 0.0, 1.0), (0.75, 0, 10.0, 11.0)]
+    rows = (u('u') & ConstantSampler(-5.0)) | 3.0 & (u('u', low=10, high=11) & u('n', loc=20, scale=0.1))
+    dc = rows.device_columns()
+    assert [c[1] for c in dc] == [id(rows)] * 2 and dc[1][2] == [(1.0, 2, -5.0, 0.0), (3.0, 1, 20.0, 0.1)]
+    three = (u('u') | u('u', low=2, high=3)) | 2.0 & u('u', low=4, high=5)
+    dc = three.device_columns()
+    assert [round(c[0], 6) for c in dc[0][2]] == [1.0, 1.0, 2.0] and len({c[1] for c in dc}) == 1
+    five = ((u('u') | u('u')) | (u('u') | u('u'))) | u('u')
+    assert five.device_columns() is None                           # more than 4 components: host sampling
+    both = mix & u('u') & (u('n') | ConstantSampler(1.0))
+    dc = both.device_columns()
+    assert [c[0] for c in dc] == ['mix', 0, 'mix'] and dc[0][1] != dc[2][1]
+    assert (mix + 1.0).device_columns() is None and ((u('u') & mix) | u('u', dim=2)).device_columns() is None
+    from pydens_b200 import _native as N
+    arr = N.make_columns(both.device_columns(), 3)
+    assert (arr[0].kind, arr[0].group, arr[0].n_comp, arr[2].group, arr[1].kind) == (3, 0, 2, 1, 0)
+    assert abs(arr[0].cum_w[0] - 0.25) < 1e-7 and arr[0].cum_w[1] == 1.0
