@@ -29,6 +29,14 @@ struct float2 { float x, y; };
 inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 #endif
 
+// Unroll factors of the inner loops for many-channel (C >= 8) problems, whose per-point state lives in global memory.
+#ifndef PINN_UNR_WIDE
+#define PINN_UNR_WIDE 4
+#endif
+#ifndef PINN_BWD_UNR_WIDE
+#define PINN_BWD_UNR_WIDE 1
+#endif
+
 // Packed FP32x2 arithmetic: Blackwell's FFMA2 / FMUL2 do two fp32 operations per issued instruction
 // (the scalar operand is broadcast by the instruction itself).  The inner loops keep their accumulators
 // as pairs of neighbouring output units, which halves the FMA instruction count.
@@ -362,7 +370,7 @@ PINN_HD void fwd_block_hidden(const float* __restrict__ Wt, int wt_stride, const
     // many-channel problems keep their per-point state in global memory: more iterations in flight overlap
     // the load latency there (measured: cfg5 -10 %), while for the shared-memory-resident narrow problems
     // unrolling only costs instruction-cache reach (cfg2 +7 %)
-    constexpr int UNR = (C >= 8) ? 4 : ((C >= 6) ? 2 : 1);
+    constexpr int UNR = (C >= 8) ? PINN_UNR_WIDE : ((C >= 6) ? 2 : 1);
 #pragma unroll UNR
     for (int k = 0; k < n_in; ++k) {
         float a[C];
@@ -940,7 +948,8 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
             }
         }
 
-#pragma unroll 1
+        constexpr int BUNR = (C >= 8) ? PINN_BWD_UNR_WIDE : 1;
+#pragma unroll BUNR
         for (int j0 = 0; j0 < L.n_out; j0 += JJ) {
             float v[JJ * JB];
 #pragma unroll
