@@ -1,0 +1,123 @@
+""" Randomised cross-check of the per-thread device code (host build, tests/emul) against the fp64 autograd
+oracle: random network shapes (widths 1..40, so every output-block / input-block remainder and several blocks
+per layer occur), activations, residual layouts, ansatz configurations, domains and equations.  CPU only. """
+import numpy as np
+import pytest
+import torch
+
+import emul_harness as E
+import problems as P
+from helpers import rel_l2
+from oracle import autograd_port as ap
+from pydens_b200 import _native as N
+from pydens_b200 import tracer as T
+
+ACTS = ['Tanh', 'Sigmoid', P.Sin, 'Softplus', 'SiLU', 'GELU']
+
+
+def _equations(total, ndims):
+    """ (name, callable(u, *xs, D, V)) candidates for a problem with `total` point columns. """
+    eqs = [('first', lambda u, *xs, D, V: D(u, xs[0]) - torch.cos(xs[0]) * u),
+           ('second', lambda u, *xs, D, V: D(D(u, xs[0]), xs[0]) + 0.5 * D(u, xs[0]) - u ** 2 + 1.0),
+           ('var', lambda u, *xs, D, V: D(u, xs[0]) * V('k', 0.7) - torch.sin(xs[0]) + V('k', 0.7) ** 2)]
+    if total >= 2:
+        j = total - 1
+        eqs += [('laplace', lambda u, *xs, D, V: D(D(u, xs[0]), xs[0]) + D(D(u, xs[j]), xs[j]) - xs[j] * u),
+                ('mixed', lambda u, *xs, D, V: D(D(u, xs[0]), xs[j]) + D(u, xs[j]) * u - 0.3),
+                ('advect', lambda u, *xs, D, V: D(u, xs[j]) + xs[0] * D(u, xs[0]) - torch.exp(-u))]
+    if total >= 3:
+        eqs += [('three', lambda u, *xs, D, V: D(D(u, xs[0]), xs[0]) + D(D(u, xs[1]), xs[1]) - D(u, xs[2])
+                 + 0.1 * D(D(u, xs[0]), xs[1]))]
+    return eqs
+
+
+def _random_problem(seed):
+    rng = np.random.RandomState(seed)
+    ndims = int(rng.randint(1, 4))
+    nparams = int(rng.randint(0, 2)) if ndims < 3 else 0
+    total = ndims + nparams
+    depth = int(rng.randint(1, 5))                               # hidden layers
+    widths = [int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 23, 31, 32, 33, 40])) for _ in range(depth)]
+    acts = [ACTS[int(rng.randint(len(ACTS)))] for _ in range(depth)]
+    layout, skip_done = '', False
+    for l in range(depth):
+        # a residual block 'R fa+' needs equal widths on both ends of the skip
+        if l >= 1 and not skip_done and widths[l] == widths[l - 1] and rng.rand() < 0.7:
+            layout += 'R fa+ '
+            skip_done = True
+        elif l >= 1 and not skip_done and rng.rand() < 0.35:
+            widths[l] = widths[l - 1]
+            layout += 'R fa+ '
+            skip_done = True
+        else:
+            layout += 'fa '
+    layout += 'f'
+    has_ic = bool(rng.rand() < 0.5)
+    nsp = ndims - 1 if has_ic else ndims
+    ic = None
+    if has_ic:
+        kind = int(rng.randint(3))
+        if kind == 0 or nsp == 0:
+            ic = float(np.round(rng.uniform(-1, 2), 2))
+        elif kind == 1:
+            ic = lambda *x: torch.sin(2.0 * x[0]) + 0.5
+        else:
+            ic = lambda *x: x[0] * (1.0 - x[-1]) + 0.25
+    bc = float(np.round(rng.uniform(-1, 1), 2)) if (nsp > 0 and rng.rand() < 0.6) else None
+    domain = [(float(np.round(rng.uniform(-1, 0.2), 2)), float(np.round(rng.uniform(0.8, 2.5), 2))) for _ in range(ndims)]
+    eqs = _equations(total, ndims)
+    name, eq = eqs[int(rng.randint(len(eqs)))]
+    ranges = domain + [(0.5, 2.0)] * nparams
+    return dict(ndims=ndims, nparams=nparams, total=total, features=widths + [1], acts=acts, layout=layout,
+                ic=ic, bc=bc, domain=domain, eq=eq, eq_name=name, ranges=ranges, variables={'k': 0.7} if name == 'var' else None,
+                log_scale=float(np.round(rng.uniform(-0.5, 0.5), 2)))
+
+
+def _layer_plan(cfg):
+    acts, skips, stack, i_a = [], [], [], 0
+    names = [(a if isinstance(a, str) else a.__name__).lower() for a in cfg['acts']]
+    for letter in cfg['layout'].replace(' ', ''):
+        if letter == 'f':
+            acts.append('none'); skips.append(None)
+        elif letter == 'a':
+            acts[-1] = names[i_a]; i_a += 1
+        elif letter == 'R':
+            stack.append(len(acts) - 1)
+        elif letter == '+':
+            skips[-1] = stack.pop()
+    return acts, skips
+
+
+@pytest.mark.parametrize('seed', list(range(120)))
+def test_random_problem_matches_fp64_oracle(seed):
+    cfg = _random_problem(seed)
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    nsp = cfg['ndims'] - 1 if cfg['ic'] is not None else cfg['ndims']
+    traced = T.trace(lambda u, *xs: cfg['eq'](u, *xs, D=T.sym_D, V=sym_V), cfg['total'], None,
+                     initial_condition=cfg['ic'], ndims_spatial=nsp)
+    acts, skips = _layer_plan(cfg)
+    spec = N.build_spec([cfg['total']] + cfg['features'], acts, cfg['ndims'], cfg['nparams'], cfg['bc'] is not None,
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, cfg['ic'] is not None, cfg['domain'], traced,
+                        skips=skips)
+
+    prob = ap.Problem(cfg['eq'], ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=cfg['ic'],
+                      boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
+                      activation=cfg['acts'], dtype=torch.float64, variables=cfg['variables'], seed=seed,
+                      layout=cfg['layout'])
+    with torch.no_grad():
+        prob.log_scale.fill_(cfg['log_scale'])
+    params = prob.flat_params().numpy()
+    assert spec.n_params == params.size, (spec.n_params, params.size, cfg['layout'], cfg['features'])
+
+    rng = np.random.RandomState(1000 + seed)
+    n = int(rng.choice([1, 5, 33, 70]))
+    pts = np.concatenate([rng.uniform(lo, hi, size=(n, 1)) for lo, hi in cfg['ranges']], axis=1).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params.astype(np.float32), pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float32).astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    tag = '%s %s %s acts=%s' % (cfg['eq_name'], cfg['layout'], cfg['features'], acts)
+    assert abs(loss - ref_loss) <= 2e-5 * max(abs(ref_loss), 1e-6), tag
+    assert rel_l2(residual, ref_res) <= 2e-5, tag
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4, tag
+    u = E.emul_forward(spec, params.astype(np.float32), pts)
+    assert rel_l2(u, prob.predict(pts.astype(np.float64))) <= 1e-5, tag
