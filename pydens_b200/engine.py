@@ -2,8 +2,11 @@
 per-step launch sequence and its CUDA-graph capture, data-parallel sharding.
 
 Per step (replaces reference pydens/model_torch.py:427-464):
-    pinn_step         sample + forward jets + residual + MSE + backward     (one CUDA kernel)
-    all_reduce        only when torch.distributed is initialised: sum of [grads | loss] over ranks (NCCL)
+    pinn_step         sample + forward jets + residual + MSE + backward     (one CUDA kernel); with
+                      torch.distributed initialised: pinn_step_allreduce, whose tail sums [grads | loss] over
+                      the ranks through NVLink peer memory (NCCL all_reduce only if IPC mapping is unavailable)
+    constraints       one more launch of the same kernel family per lowered constraint, added to [grads | loss]
+                      (constraints that do not lower are added by autograd)
     optimizer.step()  torch (fused, capturable Adam by default) on views of the flat buffer
     pinn_record_loss  loss -> device ring, advance the device step counter
 The sequence is captured once in a CUDA graph and replayed; nothing in it touches the host.
