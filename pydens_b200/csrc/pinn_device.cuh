@@ -889,8 +889,27 @@ struct GradSink {
     }
 };
 
+// Bias gradients of a layer on their own: for layers whose input width is a multiple of the reduction block
+// (the bias column would open a block of its own) and for an input layer with PINN_MAX_DIMS columns.
+template <int NF, int NS>
+PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, int RS, const GradSink& sink) {
+    constexpr int C = 1 + NF + NS;
+#pragma unroll 1
+    for (int j0 = 0; j0 < L.n_out; j0 += 32) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int j = j0 + i < L.n_out ? j0 + i : L.n_out - 1;
+            v[i] = out_rows[(size_t)j * C * RS];
+        }
+        emit_entries<32>(v, [&](int e, float t) {
+            sink.add_if(j0 + e < L.n_out, L.b_off + j0 + e, t);
+        });
+    }
+}
+
 // Reverse of linear layer L (its output adjoints zb_L are already stored in out_rows):
-//   weight AND bias gradients of L (the bias is column n_in of the same reduction batches: its
+//   weight AND bias gradients of L (the bias is normally column n_in of the same reduction batches: its
 //   "input jet" is (1, 0, …)) and — fused in the same loop — the adjoints of the layer below, pushed
 //   through that layer's activation and written over its stored jet in place.
 // JJ = output units per reduction batch (4 normally, 1 for the single-output top layer).
@@ -910,7 +929,10 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
     const ActC below = make_actc(below_act_id);
     const ActC load_act = make_actc(SKIP ? load_act_id : below_act_id);
     if (!SKIP) load_rows = in_rows;
-    const int n_cols = L.n_in + 1;                        // + bias column
+    // the bias rides as column n_in of the last block — unless n_in fills its blocks exactly: an extra block for
+    // one column would cost 1/8 of a 64-wide layer's reverse work, a separate pass over channel 0 costs ~nothing
+    const bool fold_bias = (L.n_in & (JB - 1)) != 0;
+    const int n_cols = L.n_in + (fold_bias ? 1 : 0);
 #pragma unroll 1
     for (int m0 = 0; m0 < n_cols; m0 += JB) {
         // neighbouring input units are kept as pairs: one FFMA2 serves two of them
@@ -1006,24 +1028,7 @@ PINN_HD void bwd_layer(const DevLayer& L, int below_act_id, const float* __restr
             }
         }
     }
-}
-
-// Bias gradients of a layer on their own (only the input layer with PINN_MAX_DIMS columns needs it).
-template <int NF, int NS>
-PINN_HD void bias_grad(const DevLayer& L, const float* __restrict__ out_rows, int RS, const GradSink& sink) {
-    constexpr int C = 1 + NF + NS;
-#pragma unroll 1
-    for (int j0 = 0; j0 < L.n_out; j0 += 32) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int j = j0 + i < L.n_out ? j0 + i : L.n_out - 1;
-            v[i] = out_rows[(size_t)j * C * RS];
-        }
-        emit_entries<32>(v, [&](int e, float t) {
-            sink.add_if(j0 + e < L.n_out, L.b_off + j0 + e, t);
-        });
-    }
+    if (!fold_bias) bias_grad<NF, NS>(L, out_rows, RS, sink);
 }
 
 // Weight (and bias) gradients of the FIRST linear layer: its input jet is (x, e_dir, 0); the bias rides
