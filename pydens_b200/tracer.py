@@ -357,6 +357,18 @@ _NP_UNARY = {np.sin: 'sin', np.cos: 'cos', np.tan: 'tan', np.exp: 'exp', np.log:
 _NP_BINARY = {np.add: add, np.subtract: sub, np.multiply: mul, np.divide: div, np.true_divide: div,
               np.power: power}
 
+# functions expressed through the opcodes above (no opcode of their own)
+_REWRITES = {
+    'square': lambda a: powi(a, 2),
+    'reciprocal': lambda a: div(ONE, a),
+    'rsqrt': lambda a: div(ONE, unary('sqrt', a)),
+    'sinh': lambda a: mul(const(0.5), sub(unary('exp', a), unary('exp', neg(a)))),
+    'cosh': lambda a: mul(const(0.5), add(unary('exp', a), unary('exp', neg(a)))),
+    'exp2': lambda a: unary('exp', mul(const(math.log(2.0)), a)),
+    'log2': lambda a: mul(const(1.0 / math.log(2.0)), unary('log', a)),
+    'log10': lambda a: mul(const(1.0 / math.log(10.0)), unary('log', a)),
+}
+
 
 class Sym:
     """ Symbolic stand-in for an `[N, 1]` tensor inside a traced callable. """
@@ -390,6 +402,13 @@ class Sym:
     def abs(self): return Sym(unary('abs', self.expr))
     def pow(self, o): return self.__pow__(o)
     def square(self): return Sym(powi(self.expr, 2))
+    def tan(self): return Sym(unary('tan', self.expr))
+    def sigmoid(self): return Sym(unary('sigmoid', self.expr))
+    def sinh(self): return Sym(_REWRITES['sinh'](self.expr))
+    def cosh(self): return Sym(_REWRITES['cosh'](self.expr))
+    def reciprocal(self): return Sym(div(ONE, self.expr))
+    def rsqrt(self): return Sym(_REWRITES['rsqrt'](self.expr))
+    def neg(self): return Sym(neg(self.expr))
     def view(self, *shape): return self
     def reshape(self, *shape): return self
     def float(self): return self
@@ -427,10 +446,8 @@ class Sym:
             return Sym(unary(_TORCH_UNARY[name], _as_expr(args[0])))
         if name in _TORCH_BINARY and len(args) == 2:
             return Sym(_TORCH_BINARY[name](_as_expr(args[0]), _as_expr(args[1])))
-        if name == 'square' and len(args) == 1:
-            return Sym(powi(_as_expr(args[0]), 2))
-        if name == 'reciprocal' and len(args) == 1:
-            return Sym(div(ONE, _as_expr(args[0])))
+        if name in _REWRITES and len(args) == 1:
+            return Sym(_REWRITES[name](_as_expr(args[0])))
         if name in ('zeros_like', 'ones_like') and len(args) == 1:
             return Sym(ZERO if name == 'zeros_like' else ONE)
         raise NotLowerable('torch.%s is not supported by the fused path' % name)
@@ -442,8 +459,8 @@ class Sym:
             return Sym(unary(_NP_UNARY[ufunc], _as_expr(inputs[0])))
         if ufunc in _NP_BINARY and len(inputs) == 2:
             return Sym(_NP_BINARY[ufunc](_as_expr(inputs[0]), _as_expr(inputs[1])))
-        if ufunc is np.square:
-            return Sym(powi(_as_expr(inputs[0]), 2))
+        if ufunc.__name__ in _REWRITES and len(inputs) == 1:
+            return Sym(_REWRITES[ufunc.__name__](_as_expr(inputs[0])))
         raise NotLowerable('numpy.%s is not supported by the fused path' % ufunc.__name__)
 
 

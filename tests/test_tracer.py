@@ -145,3 +145,30 @@ def test_mixed_derivative_is_polarised_onto_a_diagonal_direction():
     outs = T.run_program(tr.eq_prog, ujet, np.zeros((2, n)), [])
     np.testing.assert_allclose(outs[0], 0.5 * (ujet[6] - ujet[4] - ujet[5]), rtol=1e-12)
     np.testing.assert_allclose(outs[1 + 6], 0.5 * np.ones(n)); np.testing.assert_allclose(outs[1 + 4], -0.5 * np.ones(n))
+
+
+def test_rewritten_functions_match_torch():
+    """ sinh / cosh / exp2 / log2 / log10 / rsqrt / square / reciprocal have no opcode of their own: they lower
+    through exp / log / sqrt; value and partials must match torch's. """
+    def eq(u, x, y, D=T.sym_D):
+        return (torch.sinh(u) * np.cosh(x) + torch.exp2(y) - torch.log2(x + 2.0) + torch.log10(y + 3.0)
+                + (x + 1.5).rsqrt() * D(u, x) + u.cosh() - torch.square(D(u, y)) + torch.reciprocal(y + 2.0) + (-u).sinh())
+    tr = T.trace(lambda u, x, y: eq(u, x, y), 2, None)
+    assert tr.nf == 2 and tr.ns == 0
+    rng = np.random.RandomState(3)
+    n = 50
+    jet = rng.uniform(-1, 1, size=(3, n))
+    coords = rng.uniform(0, 1, size=(2, n))
+    outs = T.run_program(tr.eq_prog, jet, coords, [])
+
+    ch = [torch.tensor(jet[c], dtype=torch.float64, requires_grad=True) for c in range(3)]
+    x, y = (torch.tensor(coords[k], dtype=torch.float64) for k in range(2))
+    col = {d: 1 + i for i, d in enumerate(tr.dirs)}            # channel of du/dx_k
+
+    def D_num(v, xx):
+        return ch[col[0]] if xx is x else ch[col[1]]
+    r = eq(ch[0], x, y, D=D_num)
+    assert np.allclose(outs[0], r.detach().numpy(), rtol=1e-12, atol=1e-12)
+    grads = torch.autograd.grad(r.sum(), ch)
+    for c in range(3):
+        assert np.allclose(outs[1 + c], grads[c].numpy(), rtol=1e-10, atol=1e-12)
