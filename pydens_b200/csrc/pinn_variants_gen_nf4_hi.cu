@@ -1,0 +1,6 @@
+// step_kernel instantiations for NF = 4 first-order directions, general problems, NS = 3..4 (see pinn_variants.inc)
+#define PINN_VARIANT_NF 4
+#define PINN_VARIANT_GEN 1
+#define PINN_VARIANT_NS_LO 3
+#define PINN_VARIANT_NAME pinn_variants_gen_nf4_hi
+#include "pinn_variants.inc"

@@ -67,3 +67,34 @@ def test_library_is_sm100a_and_stages_weights_with_tma():
     assert 'SYNCS' in out                                   # mbarrier expect_tx / try_wait
     assert out.count('SHFL.BFLY') >= 31                     # transposing butterfly of the gradient reduction
     assert 'LDS.128' in out                                 # broadcast 128-bit weight loads
+
+
+def test_variant_tables_point_at_the_right_kernel_instantiations():
+    """ The step_kernel instantiations live in several translation units (one per NF, the heavy general ones split
+    by NS); the host dispatch tables must hand out exactly step_kernel<NF, NS, GMEM, MAXT, 16, GEN> for every
+    (NF, NS).  Checked on the host against the exported kernel stubs — no GPU needed. """
+    import ctypes as C
+    lib = C.CDLL(_native.LIB_PATH)
+
+    class Variant(C.Structure):
+        _fields_ = [('nf', C.c_int), ('ns', C.c_int), ('smem_fn', C.c_void_p), ('gmem_fn', C.c_void_p),
+                    ('smem_gen_fn', C.c_void_p), ('gmem_gen_fn', C.c_void_p), ('maxt', C.c_int)]
+
+    def stub(nf, ns, gmem, maxt, gen):
+        name = '_ZN4pinn11step_kernelILi%dELi%dELb%dELi%dELi16ELb%dEEEvNS_7DevPlanENS_8StepArgsE' % (nf, ns, gmem, maxt, gen)
+        return C.cast(getattr(lib, name), C.c_void_p).value
+
+    for nf in range(5):
+        for gen in (0, 1):
+            fn = getattr(lib, '_Z%dpinn_variants_%snf%di' % (17 if not gen else 21, 'gen_' if gen else '', nf))
+            fn.restype = C.POINTER(Variant)
+            fn.argtypes = [C.c_int]
+            for ns in range(nf + 1):
+                v = fn(ns).contents
+                maxt = 512 if 1 + nf + ns <= 3 else 256
+                assert (v.nf, v.ns, v.maxt) == (nf, ns, maxt)
+                smem, gmem = (v.smem_gen_fn, v.gmem_gen_fn) if gen else (v.smem_fn, v.gmem_fn)
+                assert smem == stub(nf, ns, 0, maxt, gen) and gmem == stub(nf, ns, 1, maxt, gen), (nf, ns, gen)
+                other = (v.smem_fn, v.gmem_fn) if gen else (v.smem_gen_fn, v.gmem_gen_fn)
+                assert other == (None, None)           # the sibling unit fills the other half (merged at plan creation)
+            assert not fn(nf + 1) and not fn(-1)
