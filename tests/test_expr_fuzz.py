@@ -1,0 +1,110 @@
+""" Randomised residual expressions: the tracer (symbolic D, partial derivatives, constant folding, hash-consing,
+slot reuse in the register programs) + the device interpreter (host build) against torch autograd in fp64.
+Each case draws an expression tree over u, its first / second derivatives, the point columns, constants and a
+trainable variable, with the operators the fused path supports, on a small fixed network.  CPU only. """
+import numpy as np
+import pytest
+import torch
+
+import emul_harness as E
+from helpers import rel_l2
+from oracle import autograd_port as ap
+from pydens_b200 import _native as N
+from pydens_b200 import tracer as T
+
+UNARY = [
+    ('sin', lambda t: torch.sin(t)), ('cos', lambda t: torch.cos(t)), ('tanh', lambda t: torch.tanh(t)),
+    ('exp', lambda t: torch.exp(-t * t)), ('sqrt', lambda t: torch.sqrt(t * t + 1.0)),
+    ('log', lambda t: torch.log(t * t + 0.5)), ('sigmoid', lambda t: torch.sigmoid(t)),
+    ('abs', lambda t: abs(t)), ('neg', lambda t: -t), ('sq', lambda t: t ** 2), ('cube', lambda t: t ** 3),
+    ('recip', lambda t: 1.0 / (t * t + 1.0)), ('sinh', lambda t: torch.sinh(0.5 * t)), ('cos2', lambda t: torch.cos(2.0 * t)),
+    ('powf', lambda t: (t * t + 1.0) ** 1.5), ('scale', lambda t: 0.37 * t - 0.2),
+]
+BINARY = [
+    ('add', lambda a, b: a + b), ('sub', lambda a, b: a - b), ('mul', lambda a, b: a * b),
+    ('div', lambda a, b: a / (b * b + 1.0)), ('mix', lambda a, b: 0.5 * a - 1.5 * b + 0.1),
+]
+
+
+def random_equation(rng, total):
+    """ -> (callable eq(u, *xs, D, V), description).  Leaves are created lazily so D() is called inside the trace. """
+    second = rng.rand() < 0.6
+    mixed = total >= 2 and rng.rand() < 0.3
+    use_var = rng.rand() < 0.4
+
+    def leaf():
+        kinds = ['u', 'u', 'ux', 'x', 'const'] + (['uxx'] if second else []) + (['uxy'] if mixed else []) \
+            + (['y', 'uy'] if total >= 2 else []) + (['var'] if use_var else [])
+        k = kinds[int(rng.randint(len(kinds)))]
+        c = float(np.round(rng.uniform(-2, 2), 2))
+        return (k, c)
+
+    def tree(depth):
+        if depth == 0 or rng.rand() < 0.2:
+            return ('leaf', leaf())
+        if rng.rand() < 0.45:
+            return ('un', int(rng.randint(len(UNARY))), tree(depth - 1))
+        return ('bin', int(rng.randint(len(BINARY))), tree(depth - 1), tree(depth - 1))
+
+    # make sure the residual depends on u and on a derivative
+    root = ('bin', 0, ('bin', 0, tree(int(rng.randint(2, 5))), ('leaf', ('ux', 0.0))), ('leaf', ('u', 0.0)))
+
+    def describe(t):
+        if t[0] == 'leaf':
+            return t[1][0] if t[1][0] != 'const' else str(t[1][1])
+        if t[0] == 'un':
+            return '%s(%s)' % (UNARY[t[1]][0], describe(t[2]))
+        return '%s(%s, %s)' % (BINARY[t[1]][0], describe(t[2]), describe(t[3]))
+
+    def eq(u, *xs, D, V):
+        x, y = xs[0], xs[-1]
+        cache = {}
+
+        def val(kind, c):
+            if kind == 'const':
+                return torch.tensor(c, dtype=torch.float64)        # a 0-d tensor: torch.sin(0.62) is not valid torch
+            if kind not in cache:
+                cache[kind] = {'u': lambda: u, 'x': lambda: x, 'y': lambda: y, 'ux': lambda: D(u, x),
+                               'uy': lambda: D(u, y), 'uxx': lambda: D(D(u, x), x), 'uxy': lambda: D(D(u, x), y),
+                               'var': lambda: V('k', 0.7)}[kind]()
+            return cache[kind]
+
+        def ev(t):
+            if t[0] == 'leaf':
+                return val(*t[1])
+            if t[0] == 'un':
+                return UNARY[t[1]][1](ev(t[2]))
+            return BINARY[t[1]][1](ev(t[2]), ev(t[3]))
+        return ev(root)
+    return eq, describe(root), use_var
+
+
+@pytest.mark.parametrize('seed', list(range(150)))
+def test_random_expression_matches_autograd(seed):
+    rng = np.random.RandomState(5000 + seed)
+    total = int(rng.randint(1, 3))
+    eq, text, use_var = random_equation(rng, total)
+    features, acts = [6, 5, 1], ['Tanh', 'Sigmoid']
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    try:
+        traced = T.trace(lambda u, *xs: eq(u, *xs, D=T.sym_D, V=sym_V), total, None)
+    except T.NotLowerable as exc:                          # e.g. program too long: the tracer must say so, not mis-lower
+        assert 'slots' in str(exc) or 'instructions' in str(exc) or 'directions' in str(exc), (text, exc)
+        return
+    spec = N.build_spec([total] + features, ['tanh', 'sigmoid', 'none'], total, 0, False, 0.0, False,
+                        [(0.0, 1.0)] * total, traced)
+    uses_var = 'k' in traced.var_names
+    if 'var' in text and not uses_var:
+        return                                             # the variable cancelled symbolically (k - k, 0 * k, …)
+    prob = ap.Problem(eq, ndims=total, features=features, activation=acts, dtype=torch.float64,
+                      variables={'k': 0.7} if uses_var else None, seed=seed, layout='fafaf')
+    params = prob.flat_params().numpy().astype(np.float32)
+    assert spec.n_params == params.size, text
+    pts = rng.uniform(0.05, 0.95, size=(40, total)).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params, pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
+    assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text
