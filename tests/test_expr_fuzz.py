@@ -108,3 +108,77 @@ def test_random_expression_matches_autograd(seed):
     assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
     assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
     assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text
+
+
+@pytest.mark.parametrize('seed', list(range(80)))
+def test_random_initial_condition_matches_autograd(seed):
+    """ Random `initial_condition` callables (over the spatial columns and trainable variables) in the ansatz
+    u = S(t) * net + ic(x): the kernel needs the jet of ic along every derivative direction and, with variables,
+    its partials — all produced by the tracer. """
+    rng = np.random.RandomState(9000 + seed)
+    nsp = int(rng.randint(1, 3))                           # spatial columns; the last column is time
+    total = nsp + 1
+    use_var = rng.rand() < 0.5
+
+    def tree(depth):
+        if depth == 0 or rng.rand() < 0.25:
+            kinds = ['x', 'x', 'const'] + (['y'] if nsp == 2 else []) + (['var'] if use_var else [])
+            return ('leaf', (kinds[int(rng.randint(len(kinds)))], float(np.round(rng.uniform(-2, 2), 2))))
+        if rng.rand() < 0.45:
+            return ('un', int(rng.randint(len(UNARY))), tree(depth - 1))
+        return ('bin', int(rng.randint(len(BINARY))), tree(depth - 1), tree(depth - 1))
+    root = ('bin', 0, tree(int(rng.randint(1, 4))), ('leaf', ('x', 0.0)))
+
+    def make_ic(V):
+        def ic(*xs):
+            def ev(t):
+                if t[0] == 'leaf':
+                    kind, c = t[1]
+                    return {'x': lambda: xs[0], 'y': lambda: xs[-1], 'const': lambda: torch.tensor(c, dtype=torch.float64),
+                            'var': lambda: V('amp', 0.6)}[kind]()
+                if t[0] == 'un':
+                    return UNARY[t[1]][1](ev(t[2]))
+                return BINARY[t[1]][1](ev(t[2]), ev(t[3]))
+            return ev(root)
+        return ic
+
+    def eq(u, *xs, D, V):
+        x, t = xs[0], xs[-1]
+        r = D(u, t) - 0.3 * D(D(u, x), x) + 0.1 * u * D(u, x)
+        if nsp == 2:
+            r = r - 0.2 * D(D(u, xs[1]), xs[1]) + 0.05 * D(D(u, x), xs[1])
+        return r
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    try:
+        traced = T.trace(lambda u, *xs: eq(u, *xs, D=T.sym_D, V=sym_V), total, None,
+                         initial_condition=make_ic(sym_V), ndims_spatial=nsp)
+    except T.NotLowerable as exc:                          # a jet too long for the program memory: must say so
+        assert 'slots' in str(exc) or 'instructions' in str(exc), exc
+        return
+    has_var = 'amp' in traced.var_names
+    features = [7, 6, 1]
+    bc = float(np.round(rng.uniform(-1, 1), 2)) if rng.rand() < 0.5 else None
+    domain = [(float(np.round(rng.uniform(-0.5, 0.1), 2)), float(np.round(rng.uniform(0.9, 1.8), 2))) for _ in range(total)]
+    spec = N.build_spec([total] + features, ['tanh', 'tanh', 'none'], total, 0, bc is not None, bc or 0.0, True, domain, traced)
+    holder = {}
+    prob = ap.Problem(eq, ndims=total, features=features, activation='Tanh', dtype=torch.float64,
+                      initial_condition=make_ic(lambda n, init: holder['p'].V(n, init)), boundary_condition=bc, domain=domain,
+                      variables={'amp': 0.6} if has_var else None, seed=seed, layout='fafaf')
+    holder['p'] = prob
+    if use_var and not has_var:
+        return                                             # the variable cancelled symbolically
+    with torch.no_grad():
+        prob.log_scale.fill_(float(np.round(rng.uniform(-0.5, 0.5), 2)))
+    params = prob.flat_params().numpy().astype(np.float32)
+    assert spec.n_params == params.size
+    pts = np.concatenate([rng.uniform(lo, hi, size=(40, 1)) for lo, hi in domain], axis=1).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params, pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6)
+    assert rel_l2(residual, ref_res) <= 3e-5 * cond
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond
+    u = E.emul_forward(spec, params, pts)
+    ref_u = prob.predict(pts.astype(np.float64))
+    assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max())
