@@ -85,3 +85,60 @@ def test_readme_snippets_run_unchanged_on_this_package(monkeypatch):
     frozen = [n for n, p in last.model.named_parameters() if not p.requires_grad]
     assert frozen and all(('conv_block' in n) or n == 'log_scale' for n in frozen)
     assert last.model.init.requires_grad
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/pydens/model_torch.py'), reason='reference checkout not present')
+def test_reshape_and_concat_equals_the_reference_on_random_inputs():
+    """ `Solver.reshape_and_concat` (reference model_torch.py:328-362) decides how `predict` and constraints read
+    numbers / arrays / lists / tensors: same output as the reference's own classmethod on random argument mixes. """
+    import numpy as np
+    import torch
+    here = os.path.dirname(os.path.abspath(__file__))
+    standin = os.path.join(os.path.dirname(here), 'oracle', 'batchflow_standin')
+    saved_path, saved_mods = list(sys.path), {k: sys.modules.get(k) for k in ('pydens', 'pydens.model_torch', 'batchflow')}
+    for k in list(sys.modules):
+        if k == 'pydens' or k.startswith('pydens.') or k == 'batchflow' or k.startswith('batchflow.'):
+            sys.modules.pop(k)
+    sys.path[:0] = [standin, '/root/reference']
+    try:
+        import pydens as ref
+        assert ref.__file__.startswith('/root/reference')
+        ref_fn = ref.Solver.reshape_and_concat
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k == 'pydens' or k.startswith('pydens.') or k == 'batchflow' or k.startswith('batchflow.'):
+                sys.modules.pop(k)
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
+    from pydens_b200 import Solver
+    rng = np.random.RandomState(0)
+    for case in range(200):
+        n = int(rng.choice([1, 2, 5, 16]))
+        args = []
+        for _ in range(int(rng.randint(1, 5))):
+            kind = int(rng.randint(7))
+            if kind == 0:
+                args.append(float(np.round(rng.uniform(-3, 3), 3)))
+            elif kind == 1:
+                args.append(int(rng.randint(-3, 4)))
+            elif kind == 2:
+                args.append(rng.uniform(-1, 1, size=n).astype(np.float32))
+            elif kind == 3:
+                args.append(rng.uniform(-1, 1, size=(n, 1)))
+            elif kind == 4:
+                args.append(list(np.round(rng.uniform(-1, 1, size=n), 3)))
+            elif kind == 5:
+                args.append(torch.tensor(rng.uniform(-1, 1, size=n), dtype=torch.float32))
+            else:
+                args.append(torch.tensor(rng.uniform(-1, 1, size=(n, 1)), dtype=torch.float32))
+        try:
+            want = ref_fn(list(args))
+        except Exception as exc:                            # the reference rejects the mix: so must we
+            with pytest.raises(Exception):
+                Solver.reshape_and_concat(list(args))
+            continue
+        got = Solver.reshape_and_concat(list(args))
+        assert tuple(got.shape) == tuple(want.shape), (case, [type(a).__name__ for a in args])
+        assert torch.allclose(got.to(torch.float64), want.to(torch.float64), rtol=1e-6, atol=1e-7), case
