@@ -297,7 +297,9 @@ class FusedEngine:
         zero_host = None
 
         if host_sampler is not None:
-            n_stage = 4
+            # staging depth = how many steps the host may run ahead of the GPU (absorbs host jitter; matters most
+            # with several ranks, where the in-kernel all-reduce makes every rank wait for the slowest host)
+            n_stage = max(2, int(os.environ.get('PYDENS_B200_STAGES', '4')))
             pinned = [torch.empty((batch_size, total), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
             events = [torch.cuda.Event() for _ in range(n_stage)]          # H2D of buffer k has completed
             free_ev = [torch.cuda.Event() for _ in range(n_stage)]         # compute no longer reads dev_pts[k]
