@@ -154,6 +154,175 @@ def cpu_reference(workload, n_gpus, steps, warmup, budget_s=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# our arm: device-timed steps of one workload
+# ------------------------------------------------------------------------------------------------
+def make_solver(workload, dev):
+    import problems as P
+    from pydens_b200 import Solver, D, V
+    name, batch, lr = WORKLOADS[workload]
+    cfg = P.PROBLEMS[name]
+    torch.manual_seed(0)
+    solver = Solver(P.bind(name, D, lambda n, init: V(n, data=torch.Tensor([init]))), ndims=cfg['ndims'],
+                    nparams=cfg['nparams'], initial_condition=cfg['ic'], boundary_condition=cfg['bc'],
+                    domain=cfg['domain'], layout=cfg['layout'], features=cfg['features'],
+                    activation=cfg['activation'], device=dev, backend='fused', seed=123)
+    return solver, cfg, lr
+
+
+class Timed:
+    """ One workload on this rank's shard: an HBM-resident pool of distinct batches, the step function, and
+    device-timed runs of EXACTLY K steps (CUDA events, max over ranks), repeated `reps` times. """
+
+    def __init__(self, workload, gbatch, dev, rank, world, K, W, pool_cap_bytes=2 << 30):
+        import ctypes as C
+        from pydens_b200 import _native
+        from pydens_b200.engine import shard_batch
+        import torch.distributed as dist
+        self.dist, self.world, self.rank, self.dev, self.K, self.W = dist, world, rank, dev, K, W
+        self.solver, self.cfg, self.lr = make_solver(workload, dev)
+        self.eng = eng = self.solver._get_engine()
+        self.info = eng.info
+        self.total = self.cfg['ndims'] + self.cfg['nparams']
+        self.gbatch = gbatch
+        self.local_n, self.offset = shard_batch(gbatch, world, rank)
+        self.inv_n = 1.0 / gbatch
+        bytes_per_batch = self.local_n * self.total * 4
+        # >= 160 distinct batches at cfg2 (the pool then exceeds the 126 MB L2); big batches are each > L2 already
+        self.pool_n = int(max(2, min(max(K, 160), 256, pool_cap_bytes // max(bytes_per_batch, 1))))
+        gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+        self.pool = torch.empty((self.pool_n, self.local_n, self.total), device=dev)
+        for k, (lo, hi) in enumerate(self.cfg['ranges']):
+            self.pool[:, :, k] = torch.rand((self.pool_n, self.local_n), generator=gen, device=dev) * (hi - lo) + lo
+        self.solver._make_optimizer('Adam', self.lr, fused_hint=True)
+        self.opt = self.solver.optimizer
+        self.ring = torch.zeros(4096, device=dev)
+        self._C, self._native = C, _native
+
+    def step(self, pts):
+        C, eng = self._C, self.eng
+        eng._step(pts, None, self.local_n, self.inv_n, self.offset, allreduce=self.world > 1)
+        if self.world > 1 and eng.comm is None:
+            self.dist.all_reduce(eng.out)
+        self.opt.step()
+        self._native.check(eng.lib.pinn_record_loss(eng.plan, C.c_void_p(eng.out.data_ptr()), C.c_void_p(self.ring.data_ptr()),
+                                                    C.c_int64(self.ring.numel()), C.c_void_p(eng.step_counter.data_ptr()),
+                                                    eng._stream()))
+
+    def run(self, reps=10, sampled=False):
+        """ -> (list of ms for K steps, one per repetition; graphed?) """
+        K, dist, world, dev = self.K, self.dist, self.world, self.dev
+        for i in range(self.W):
+            self.step(None if sampled else self.pool[i % self.pool_n])
+        torch.cuda.synchronize()
+        graph, graphed = torch.cuda.CUDAGraph(), True
+        try:
+            with torch.cuda.graph(graph):
+                for i in range(K):
+                    self.step(None if sampled else self.pool[i % self.pool_n])
+        except Exception as exc:            # noqa: BLE001
+            graphed = False
+            torch.cuda.synchronize()
+            sys.stderr.write('graph capture failed (%s): timing plain launches\n' % exc)
+        if graphed:
+            graph.replay()                  # one untimed replay (uploads the graph)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            if graphed:
+                graph.replay()
+            else:
+                for i in range(K):
+                    self.step(None if sampled else self.pool[i % self.pool_n])
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            times.append(float(ms.item()))
+        del graph
+        return times, graphed
+
+    def kernel_ms(self, reps=5):
+        """ the fused kernel alone: CUDA events around K back-to-back launches on the launching stream """
+        eng, K = self.eng, self.K
+        for i in range(3):
+            eng._step(self.pool[i % self.pool_n], None, self.local_n, self.inv_n, self.offset)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = []
+        for _ in range(reps):
+            e0.record()
+            for i in range(K):
+                eng._step(self.pool[i % self.pool_n], None, self.local_n, self.inv_n, self.offset)
+            e1.record()
+            torch.cuda.synchronize()
+            best.append(e0.elapsed_time(e1) / K)
+        return sorted(best)[len(best) // 2]
+
+    def allreduce_check(self):
+        """ one step through the in-kernel peer all-reduce and through pinn_step + NCCL all_reduce on the same batch """
+        eng, dist = self.eng, self.dist
+        if self.world <= 1 or eng.comm is None:
+            return None
+        pts = self.pool[0]
+        eng._step(pts, None, self.local_n, self.inv_n, self.offset, allreduce=True)
+        torch.cuda.synchronize()
+        fused = eng.out.clone()
+        eng._step(pts, None, self.local_n, self.inv_n, self.offset, allreduce=False)
+        dist.all_reduce(eng.out)
+        torch.cuda.synchronize()
+        ref = eng.out.clone()
+        num = (fused - ref).abs().max()
+        den = ref.abs().max().clamp_min(1e-30)
+        d = (num / den).reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        return {'max_rel_diff': float(d.item()), 'vector_floats': int(fused.numel()),
+                'paths': 'pinn_step_allreduce (NVLink peer memory, in-kernel) vs pinn_step + NCCL all_reduce'}
+
+
+def roofline_blocks(t, kern_ms, step_ms, clk, peaks, workload):
+    """ roofline of the fused kernel: the binding roof (FP32 FMA for the thread kernel, tensor cores for the tile
+    kernel) first, the HBM fraction BASELINE.json asks for beside it. """
+    info = t.info
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    flops = info.flops_per_point * t.local_n
+    byts = info.bytes_per_point * t.local_n
+    ach_tf = flops / (kern_ms * 1e-3) / 1e12
+    ach_gbs = byts / (kern_ms * 1e-3) / 1e9
+    sm_mhz = (clk or {}).get('sm_mhz') or float(peaks.get('sm_max_mhz', 1965.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(workload)
+    except (OSError, ValueError):
+        pass
+    if info.tensor_core:
+        bf16 = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
+        peak = bf16 / 2.0
+        roof = {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach_tf / peak,
+                'traffic': traffic, 'kernel': 'wide_step_kernel (tcgen05 kind::tf32, 3xTF32)', 'kernel_ms': kern_ms,
+                'share_of_step': kern_ms / step_ms, 'flops_per_point': int(info.flops_per_point),
+                'peak_source': 'dense TF32 = measured cuBLAS bf16 (sustained) / 2, ' + peak_src,
+                'note': 'achieved counts the ALGORITHMIC 6*C*M flops per point once; the tensor cores execute 3x that '
+                        '(3xTF32 split for fp32-grade results), so the pipe utilisation is ~3x frac'}
+    else:
+        peak = info.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roof = {'bound': 'fp32', 'achieved': ach_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach_tf / peak,
+                'traffic': traffic, 'kernel': 'step_kernel', 'kernel_ms': kern_ms, 'share_of_step': kern_ms / step_ms,
+                'flops_per_point': int(info.flops_per_point),
+                'peak_source': '%d SMs x 128 FMA lanes x 2 x %.0f MHz (SM clock sampled under load)' % (info.sm_count, sm_mhz)}
+    hbm = {'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'peak_source': peak_src,
+           'bytes_per_point': int(info.bytes_per_point),
+           'note': 'reported because BASELINE.json asks for it: the path is compute bound (flop/byte ~1e3-4e4)'}
+    return roof, hbm
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument('--gpus', type=int, default=1)
@@ -165,15 +334,14 @@ def main():
                      help='fix the GLOBAL batch (strong scaling); default: per-GPU batch of the workload (weak)')
     ap_.add_argument('--no-cpu-baseline', action='store_true')
     ap_.add_argument('--no-e2e', action='store_true')
+    ap_.add_argument('--no-extras', action='store_true', help='skip strong_cfg5 / other_configs')
+    ap_.add_argument('--reps', type=int, default=10, help='repetitions of the K-step timed region (min/median/max)')
     args = ap_.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     os.environ.setdefault('PYDENS_B200_PROGRESS', '0')
-    if 'PYDENS_B200_NCCL_DEBUG' not in os.environ:                 # keep stdout to the one JSON line
-        os.environ.pop('NCCL_DEBUG', None)
-        os.environ['NCCL_DEBUG_FILE'] = '/dev/null'
 
     if args.impl == 'reference':
         if rank != 0:
@@ -199,121 +367,42 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dev = torch.device('cuda', local_rank)
 
-    import ctypes as C
-    import problems as P
-    from pydens_b200 import Solver, D, V, _native
     name, batch, lr = WORKLOADS[args.workload]
-    cfg = P.PROBLEMS[name]
     gbatch = args.global_batch if args.global_batch else batch * world
-    torch.manual_seed(0)
-    solver = Solver(P.bind(name, D, lambda n, init: V(n, data=torch.Tensor([init]))), ndims=cfg['ndims'],
-                    nparams=cfg['nparams'], initial_condition=cfg['ic'], boundary_condition=cfg['bc'],
-                    domain=cfg['domain'], layout=cfg['layout'], features=cfg['features'],
-                    activation=cfg['activation'], device=dev, backend='fused', seed=123)
-    eng = solver._get_engine()
-    info = eng.info
-    total = cfg['ndims'] + cfg['nparams']
-    from pydens_b200.engine import shard_batch
-    local_n, offset = shard_batch(gbatch, world, rank)
-    inv_n = 1.0 / gbatch
 
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
 
-    # ---------------- value: K graph-replayed steps over an HBM-resident pool of batches ----------------
-    pool_n = min(max(K, 160), 256)          # >= 160 distinct batches: the pool (>= 128 MB at cfg2) exceeds the 126 MB L2
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    pool = torch.empty((pool_n, local_n, total), device=dev)
-    for k, (lo, hi) in enumerate(cfg['ranges']):
-        pool[:, :, k] = torch.rand((pool_n, local_n), generator=gen, device=dev) * (hi - lo) + lo
-    solver._make_optimizer('Adam', lr, fused_hint=True)
-    opt = solver.optimizer
-    ring = torch.zeros(K + W + 8, device=dev)
-
-    def step(i, pts):
-        eng._step(pts, None, local_n, inv_n, offset, allreduce=world > 1)
-        if world > 1 and eng.comm is None:
-            dist.all_reduce(eng.out)
-        opt.step()
-        _native.check(eng.lib.pinn_record_loss(eng.plan, C.c_void_p(eng.out.data_ptr()), C.c_void_p(ring.data_ptr()),
-                                               C.c_int64(ring.numel()), C.c_void_p(eng.step_counter.data_ptr()),
-                                               eng._stream()))
-    for i in range(W):
-        step(i, pool[i % pool_n])
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    graphed = True
-    try:
-        with torch.cuda.graph(graph):
-            for i in range(K):
-                step(i, pool[i % pool_n])
-    except Exception as exc:            # noqa: BLE001
-        graphed = False
-        torch.cuda.synchronize()
-        sys.stderr.write('graph capture failed (%s): timing plain launches\n' % exc)
-    if graphed:
-        graph.replay()                  # one untimed replay (uploads the graph), then the timed one
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # ---------------- value: K graph-replayed steps over an HBM-resident pool of batches, `reps` times ----------
+    t = Timed(args.workload, gbatch, dev, rank, world, K, W)
+    eng, info, total, local_n = t.eng, t.info, t.total, t.local_n
+    check = t.allreduce_check()
     t_load0 = time.time()
-    e0.record()
-    if graphed:
-        graph.replay()
-    else:
-        for i in range(K):
-            step(i, pool[i % pool_n])
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    times, graphed = t.run(reps=args.reps)
+    ms_sorted = sorted(times)
+    ms_total = ms_sorted[len(ms_sorted) // 2]                       # median of the repetitions
     value = gbatch * K / (ms_total * 1e-3)
     last_loss = float(eng.out[eng.n_params].item())
 
     # ---------------- in-kernel sampling variant (the default `fit(sampler=None)` mode) ----------------
-    graph2 = torch.cuda.CUDAGraph()
     sampled_value = None
     try:
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph2):
-            for i in range(K):
-                step(i, None)
-        graph2.replay()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0.record(); graph2.replay(); e1.record()
-        torch.cuda.synchronize()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        sampled_value = gbatch * K / (float(ms2.item()) * 1e-3)
+        ts, _ = t.run(reps=3, sampled=True)
+        sampled_value = gbatch * K / (sorted(ts)[1] * 1e-3)
     except Exception as exc:            # noqa: BLE001
         torch.cuda.synchronize()
-        sys.stderr.write('sampled-variant graph failed: %s\n' % exc)
+        sys.stderr.write('sampled-variant run failed: %s\n' % exc)
 
     # ---------------- roofline: the fused kernel alone ----------------
-    for i in range(3):
-        eng._step(pool[i % pool_n], None, local_n, inv_n, offset)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(K):
-        eng._step(pool[i % pool_n], None, local_n, inv_n, offset)
-    e1.record()
-    torch.cuda.synchronize()
-    kern_ms = e0.elapsed_time(e1) / K
+    kern_ms = t.kernel_ms()
     t_load1 = time.time()
 
     # ---------------- e2e: Solver.fit with host batches (pinned H2D per step, loss D2H per step) --------
     e2e = None
     if not args.no_e2e:
-        host_pool = [torch.empty((gbatch, total)).pin_memory() for _ in range(min(K, 32))]
+        solver, cfg = t.solver, t.cfg
+        host_pool = [torch.empty((gbatch, total)).pin_memory() for _ in range(min(max(K, 8), 32))]
         for hp in host_pool:
             for k, (lo, hi) in enumerate(cfg['ranges']):
                 hp[:, k] = torch.rand(gbatch) * (hi - lo) + lo
@@ -325,79 +414,119 @@ def main():
                 self.i += 1
                 return host_pool[self.i % len(host_pool)]
         hb = HostBatches()
-        solver.fit(niters=W, batch_size=gbatch, sampler=hb, lr=lr)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        solver.fit(niters=K, batch_size=gbatch, sampler=hb, lr=lr)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {'value': gbatch * K / float(dt.item()), 'unit': 'points/s',
+        solver.fit(niters=max(W, 8), batch_size=gbatch, sampler=hb, lr=lr)      # warm-up: also builds the step graphs
+        e2e_times = []
+        for _ in range(max(3, args.reps // 2)):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            solver.fit(niters=K, batch_size=gbatch, sampler=hb, lr=lr)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e_times.append(float(dt.item()))
+        dt_med = sorted(e2e_times)[len(e2e_times) // 2]
+        e2e = {'value': gbatch * K / dt_med, 'unit': 'points/s',
                'h2d_bytes_per_step': int(local_n * total * 4) * world, 'd2h_bytes_per_step': 4 * world,
-               'ms_per_step': 1e3 * float(dt.item()) / K,
-               'api': 'Solver.fit(niters=K, batch_size=B, sampler=<host batches in pinned memory>)'}
+               'ms_per_step': 1e3 * dt_med / K,
+               'ms_per_step_min_median_max': [1e3 * min(e2e_times) / K, 1e3 * dt_med / K, 1e3 * max(e2e_times) / K],
+               'repetitions': len(e2e_times),
+               'api': 'Solver.fit(niters=K, batch_size=B, sampler=<host batches in pinned memory>), wall clock around the '
+                      'call incl. its final synchronisation; every step: one H2D copy of the batch, one D2H read of the loss'}
 
     clk = clocks.stop(t_load0, t_load1) if clocks else None
-    del graph, graph2                    # graphs hold captured NCCL work: drop them before tearing NCCL down
+
+    # ---------------- the other BASELINE configurations (N=1) and cfg5 strong scaling (4 M points over N GPUs) --------
+    other, strong = None, None
+    if not args.no_extras and args.workload == 'cfg2' and not args.global_batch:
+        kk = max(3, min(K, 10))
+        del t.pool
+        torch.cuda.empty_cache()
+        try:
+            ts5 = Timed('cfg5', 4000000, dev, rank, world, kk, 3, pool_cap_bytes=1 << 30)
+            tms, _ = ts5.run(reps=3)
+            med = sorted(tms)[1]
+            strong = {'workload': 'cfg5 wave3d, MLP [4, 64, 64, 64, 64, 1] Tanh', 'global_batch': 4000000, 'n_gpus': world,
+                      'scaling': 'strong', 'steps': kk, 'ms_per_step': med / kk, 'value': 4000000 * kk / (med * 1e-3),
+                      'unit': 'points/s', 'kernel': 'tcgen05 tile kernel' if ts5.info.tensor_core else 'thread kernel',
+                      'allreduce_check': ts5.allreduce_check(),
+                      'note': 'same code at every N: the driver can form the 1->N strong-scaling ratio from these lines'}
+            del ts5
+            torch.cuda.empty_cache()
+        except Exception as exc:        # noqa: BLE001
+            strong = {'error': str(exc)[:200]}
+        if world == 1:
+            other = {}
+            for wl in ('cfg3', 'cfg4', 'cfg5'):
+                try:
+                    tw = Timed(wl, WORKLOADS[wl][1], dev, rank, world, kk, 3, pool_cap_bytes=1 << 30)
+                    tms, _ = tw.run(reps=3)
+                    med = sorted(tms)[1] / kk
+                    km = tw.kernel_ms(reps=3)
+                    roof, _ = roofline_blocks(tw, km, med, clk, _peaks(), wl)
+                    other[wl] = {'workload': describe(wl, 1)['workload'], 'ms_per_step': med,
+                                 'value': WORKLOADS[wl][1] / (med * 1e-3), 'unit': 'points/s', 'steps': kk,
+                                 'roofline': {k: roof[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic', 'kernel_ms')}}
+                    del tw
+                    torch.cuda.empty_cache()
+                except Exception as exc:        # noqa: BLE001
+                    other[wl] = {'error': str(exc)[:200]}
+
     torch.cuda.synchronize()
     if rank != 0:
         _shutdown(dist, world)
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except (OSError, ValueError):
-        pass
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
-    bytes_per_launch = info.bytes_per_point * local_n
-    flops_per_launch = info.flops_per_point * local_n
-    ach_gbs = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-    sm_mhz = (clk or {}).get('sm_mhz') or float(peaks.get('sm_max_mhz', 1965.0))
-    fp32_peak = info.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
-    ach_tf = flops_per_launch / (kern_ms * 1e-3) / 1e12
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload)
-    except (OSError, ValueError):
-        pass
-
+    peaks = _peaks()
+    roof, hbm = roofline_blocks(t, kern_ms, ms_total / K, clk, peaks, args.workload)
+    n_ctas = min(info.sm_count, (local_n + 127) // 128) if info.tensor_core else \
+        min(info.sm_count, (local_n + info.threads_per_cta - 1) // info.threads_per_cta)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'points/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_total / K, 'higher_is_better': True,
         'scaling': 'strong' if args.global_batch else 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
+        'timing': {'repetitions': len(times), 'ms_per_step_min': ms_sorted[0] / K, 'ms_per_step_median': ms_total / K,
+                   'ms_per_step_max': ms_sorted[-1] / K, 'value_is': 'median over repetitions of K graph-replayed steps'},
         'config': dict(describe(args.workload, world), global_batch=gbatch,
                        inputs='HBM-resident pool of %d distinct batches (%.0f MB%s), one per step; '
                               'in-kernel Philox sampling variant reported as value_sampled'
-                              % (pool_n, pool.numel() * 4 / 1e6, ' > L2' if pool.numel() * 4 > 126e6 else ''),
+                              % (t.pool_n, t.pool_n * local_n * total * 4 / 1e6,
+                                 ' > L2' if t.pool_n * local_n * total * 4 > 126e6 else ''),
                        cuda_graph=graphed, final_loss=last_loss,
                        allreduce=('in-kernel over NVLink peer memory (pinn_step_allreduce)' if eng.comm is not None
                                   else ('NCCL' if world > 1 else 'none')),
-                       kernel='step_kernel<NF=%d,NS=%d> %d threads/CTA x %d CTAs, %d B smem, %d regs, activations in %s'
-                              % (info.nf, info.ns, info.threads_per_cta, min(info.sm_count, (local_n + info.threads_per_cta - 1) // info.threads_per_cta),
-                                 info.smem_bytes, info.regs_per_thread, 'smem' if info.activations_in_smem else 'gmem')),
+                       kernel='%s<NF=%d,NS=%d> %d threads/CTA x %d CTAs, %d B smem, %d regs, per-point state in %s'
+                              % ('wide_step_kernel' if info.tensor_core else 'step_kernel', info.nf, info.ns,
+                                 info.threads_per_cta, n_ctas, info.smem_bytes, info.regs_per_thread,
+                                 'TMEM + L2 slab' if info.tensor_core else ('smem' if info.activations_in_smem else 'gmem'))),
         'value_sampled': sampled_value,
         'gpu_launches': 2 * K,
         'clocks': clk,
-        'roofline': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
-                     'traffic': traffic, 'kernel': 'step_kernel', 'kernel_ms': kern_ms,
-                     'share_of_step': kern_ms / (ms_total / K), 'peak_source': peak_src,
-                     'note': 'path is FP32-FMA bound (flop/byte ~1e3): see fp32'},
-        'fp32': {'achieved': ach_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / fp32_peak,
-                 'flops_per_point': int(info.flops_per_point),
-                 'peak_source': '%d SMs x 128 FMA lanes x 2 x %.0f MHz (SM clock sampled under load)' % (info.sm_count, sm_mhz)},
+        'roofline': roof,
+        'hbm': hbm,
         'e2e': e2e,
     }
+    if check is not None:
+        line['allreduce_check'] = check
+    if strong is not None:
+        line['strong_cfg5'] = strong
+    if other is not None:
+        line['other_configs'] = other
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference(args.workload, 1, 40, 2, budget_s=20.0)
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)
     _shutdown(dist, world)
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        return {}
 
 
 def _shutdown(dist, world):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   8
+#define PINN_ABI_VERSION   9
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -255,7 +255,8 @@ int pinn_step(const PinnPlan* plan,
  *                      (peer stores), publishes an arrival flag (release, system scope), waits for the
  *                      flags of all ranks and sums the slots in rank order, so every rank holds
  *                      bit-identical results.  All ranks must issue the same sequence of calls.  If a
- *                      peer does not arrive within ~4 s the outputs are set to NaN instead of hanging.
+ *                      peer does not arrive within PINN_COMM_TIMEOUT_S (default 60) seconds the outputs are set to NaN instead of
+ *                      hanging; pinn_comm_status reports (and clears) that condition.
  */
 #define PINN_COMM_HANDLE_BYTES 64
 #define PINN_COMM_MAX_RANKS     8
@@ -270,6 +271,41 @@ int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm,
                         uint64_t point_offset, int64_t n_points, float inv_global_n,
                         float* grads_and_loss, float* residual_out,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Health of the peer all-reduce: *aborted != 0 after a peer failed to arrive within the time limit (the step's
+ * outputs were poisoned with NaN and the flag is sticky).  Host-synchronous (one 4-byte D2H); call it after a fit,
+ * not per step.  `reset` != 0 clears the flag.  PINN_COMM_TIMEOUT_S in the environment sets the limit (default 60 s). */
+int pinn_comm_status(PinnComm* comm, int* aborted, int reset);
+
+/*
+ * Host-batch pipeline: the per-step HOST work of the reference loop when the points come from a host sampler —
+ * `sampler.sample(batch_size)` -> tensors on the device (model_torch.py:433-437) and `losses.append(loss.cpu())`
+ * (:464) — as ONE native call per step.  The pipe owns `n_stage` device staging buffers ([local_n, total] fp32),
+ * a copy stream and a read-back stream:
+ *
+ *   pinn_pipe_step(pipe, slot, host_points, graph_exec, ring_src, loss_dst, stream)
+ *       1. copy stream: wait until the compute stream no longer reads staging buffer `slot`, then
+ *          cudaMemcpyAsync(host_points -> buffer[slot])            (host_points: local_n*total floats, pinned);
+ *       2. `stream` (the compute stream) waits for that copy;
+ *       3. cudaGraphLaunch(graph_exec, stream) — the captured compute part of the step
+ *          (pinn_step on buffer[slot] + optimizer + pinn_record_loss); skipped when graph_exec is NULL
+ *          (the caller launches the step itself and then calls pinn_pipe_finish);
+ *       4. read-back stream: after the step, cudaMemcpyAsync(loss_dst <- ring_src, 4 bytes) (loss_dst pinned).
+ *   pinn_pipe_finish   steps 4 of the above for a caller-launched step (graph_exec == NULL).
+ *   pinn_pipe_wait     host-blocks until the H2D copy last issued for `slot` has completed (the caller may then
+ *                      overwrite the pinned source it handed in);   pinn_pipe_sync drains both side streams.
+ * Nothing here allocates per step; the calls are NOT capturable (they are the part of the step that stays outside
+ * the CUDA graph).
+ */
+typedef struct PinnPipe PinnPipe;
+int pinn_pipe_create(const PinnPlan* plan, int n_stage, int64_t local_n, PinnPipe** out);
+int pinn_pipe_destroy(PinnPipe* pipe);
+float* pinn_pipe_buffer(PinnPipe* pipe, int slot);
+int pinn_pipe_step(PinnPipe* pipe, int slot, const float* host_points, void* graph_exec,
+                   const float* ring_src, float* loss_dst, void* stream);
+int pinn_pipe_finish(PinnPipe* pipe, int slot, const float* ring_src, float* loss_dst, void* stream);
+int pinn_pipe_wait(PinnPipe* pipe, int slot);
+int pinn_pipe_sync(PinnPipe* pipe);
 
 /* Forward only: u = ansatz(net(x)) for explicit points — the work of Solver.predict
  * (model_torch.py:466-487) and of the `_forward` closure handed to constraints (:451-454).
@@ -315,6 +351,8 @@ typedef struct PinnPlanInfo {
     int32_t rows_per_point;           /* floats of per-point state kept between fwd/bwd  */
     int64_t flops_per_point;          /* algorithmic 6*C*M                */
     int32_t bytes_per_point;          /* algorithmic 4*(ndims+nparams)                   */
+    int32_t tensor_core;              /* 1: the tcgen05 / TMEM tile kernel for wide networks runs the step (3xTF32),
+                                         0: the thread-per-point FP32 kernel                 */
 } PinnPlanInfo;
 int pinn_plan_info(const PinnPlan* plan, PinnPlanInfo* info);
 

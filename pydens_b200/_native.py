@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
@@ -66,13 +66,15 @@ class PinnPlanInfo(C.Structure):
         ('rows_per_point', C.c_int32),
         ('flops_per_point', C.c_int64),
         ('bytes_per_point', C.c_int32),
+        ('tensor_core', C.c_int32),
     ]
 
 
 EXPORTS = ('pinn_last_error', 'pinn_abi_version', 'pinn_plan_create', 'pinn_plan_destroy',
            'pinn_workspace_bytes', 'pinn_out_floats', 'pinn_step', 'pinn_forward', 'pinn_sample',
            'pinn_record_loss', 'pinn_plan_info', 'pinn_comm_create', 'pinn_comm_connect', 'pinn_comm_destroy',
-           'pinn_step_allreduce')
+           'pinn_step_allreduce', 'pinn_comm_status', 'pinn_pipe_create', 'pinn_pipe_destroy', 'pinn_pipe_buffer',
+           'pinn_pipe_step', 'pinn_pipe_finish', 'pinn_pipe_wait', 'pinn_pipe_sync')
 
 LIB_PATH = os.environ.get('PYDENS_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpinn_b200.so')
 _lib = None
@@ -84,6 +86,10 @@ class NativeError(RuntimeError):
         self.code = code
 
 
+class LibraryMissing(RuntimeError):
+    """ libpinn_b200.so is absent or was built from another header. """
+
+
 def load():
     """ Load libpinn_b200.so (once).  Raises RuntimeError if it is absent or its ABI does not match:
     the fused path has no fallback. """
@@ -91,12 +97,12 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+        raise LibraryMissing('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
                            '(nvcc, sm_100a). pydens_b200 has no CPU fallback for the fit step.' % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name in EXPORTS:
         if not hasattr(lib, name):
-            raise RuntimeError('libpinn_b200.so does not export %s' % name)
+            raise LibraryMissing('libpinn_b200.so does not export %s' % name)
     lib.pinn_last_error.restype = C.c_char_p
     lib.pinn_abi_version.restype = C.c_int
     lib.pinn_plan_create.argtypes = [C.POINTER(PinnSpec), C.c_int, C.POINTER(C.c_void_p)]
@@ -111,6 +117,15 @@ def load():
     lib.pinn_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     lib.pinn_comm_connect.argtypes = [C.c_void_p, C.c_char_p]
     lib.pinn_comm_destroy.argtypes = [C.c_void_p]
+    lib.pinn_comm_status.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    lib.pinn_pipe_create.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.pinn_pipe_destroy.argtypes = [C.c_void_p]
+    lib.pinn_pipe_buffer.restype = C.c_void_p
+    lib.pinn_pipe_buffer.argtypes = [C.c_void_p, C.c_int]
+    lib.pinn_pipe_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pinn_pipe_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pinn_pipe_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.pinn_pipe_sync.argtypes = [C.c_void_p]
     lib.pinn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p]
     lib.pinn_sample.argtypes = [C.c_void_p, C.POINTER(PinnColumn), C.c_uint64, C.c_void_p, C.c_uint64,
@@ -118,7 +133,7 @@ def load():
     lib.pinn_record_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.pinn_plan_info.argtypes = [C.c_void_p, C.POINTER(PinnPlanInfo)]
     if lib.pinn_abi_version() != ABI_VERSION:
-        raise RuntimeError('libpinn_b200.so ABI %d != binding ABI %d: rebuild' % (lib.pinn_abi_version(), ABI_VERSION))
+        raise LibraryMissing('libpinn_b200.so ABI %d != binding ABI %d: rebuild' % (lib.pinn_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 
@@ -133,6 +148,8 @@ def make_columns(cols, total):
     with the same group_key share the component draw — -> ctypes array, or None for the default U[0,1). """
     if cols is None:
         return None
+    if isinstance(cols, PinnColumn * MAX_DIMS):           # already built
+        return cols
     arr = (PinnColumn * MAX_DIMS)()
     groups = {}
     for i in range(MAX_DIMS):

@@ -20,7 +20,15 @@
 #include <new>
 
 #include "pinn_step_kernel.cuh"
+#include "pinn_wide_kernel.cuh"
 #include "pinn_host_plan.h"
+
+// wide_step_kernel instantiations live in pinn_wide_nf*.cu
+pinn::StepKernelFn pinn_wide_variant_nf0(int ns);
+pinn::StepKernelFn pinn_wide_variant_nf1(int ns);
+pinn::StepKernelFn pinn_wide_variant_nf2(int ns);
+pinn::StepKernelFn pinn_wide_variant_nf3(int ns);
+pinn::StepKernelFn pinn_wide_variant_nf4(int ns);
 
 namespace pinn {
 
@@ -118,10 +126,38 @@ static bool find_variant(int nf, int ns, Variant& out) {
     return true;
 }
 
+// The tensor-core tile kernel (pinn_wide_kernel.cuh) covers plain dense chains with polynomial-family activations
+// and hidden widths <= 64; it pays off once the layers are wide enough to be real GEMMs.
+static pinn::StepKernelFn find_wide_variant(int nf, int ns) {
+    if (ns < 0 || ns > nf) return nullptr;
+    switch (nf) {
+        case 0: return pinn_wide_variant_nf0(ns);
+        case 1: return pinn_wide_variant_nf1(ns);
+        case 2: return pinn_wide_variant_nf2(ns);
+        case 3: return pinn_wide_variant_nf3(ns);
+        case 4: return pinn_wide_variant_nf4(ns);
+    }
+    return nullptr;
+}
+static bool wide_eligible(const pinn::DevPlan& h, int* max_width) {
+    if (h.n_layers < 2 || h.n_layers > pinn::wide::MAX_LAYERS) return false;
+    int mw = 0;
+    for (int l = 0; l < h.n_layers; ++l) {
+        const pinn::DevLayer& L = h.layer[l];
+        if (L.skip_src >= 0 || L.post_base >= 0) return false;
+        if (L.act != PINN_ACT_NONE && L.act != PINN_ACT_TANH && L.act != PINN_ACT_SIGMOID) return false;
+        if (l + 1 < h.n_layers) { if (L.n_out > pinn::wide::KW) return false; if (L.n_out > mw) mw = L.n_out; }
+    }
+    *max_width = mw;
+    return true;
+}
+
 struct PinnPlan {
     PinnSpec spec;
     DevPlan h;
     int device;
+    bool wide;                               // the tcgen05 tile kernel runs the step
+    StepKernelFn fn_wide;
     Variant var_store;
     const Variant* var;
     StepKernelFn fn_smem, fn_gmem;           // the pair matching this plan (plain or general)
@@ -238,6 +274,29 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); }
     }
 
+    // ---- wide networks: the tensor-core tile kernel takes the step (PINN_FORCE_KERNEL=thread|wide overrides) ----
+    {
+        p->wide = false; p->fn_wide = nullptr;
+        int mw = 0;
+        const char* fk = getenv("PINN_FORCE_KERNEL");
+        const bool eligible = wide_eligible(h, &mw);
+        bool want = eligible && mw >= 24 && (1 + s->nf + s->ns) >= 3;
+        if (fk && !strcmp(fk, "thread")) want = false;
+        if (fk && !strcmp(fk, "wide")) {
+            if (!eligible) { delete p; return fail(PINN_E_UNSUPPORTED, "PINN_FORCE_KERNEL=wide: this network is outside what the tile kernel covers"); }
+            want = true;
+        }
+        if (want) p->fn_wide = find_wide_variant(s->nf, s->ns);
+        if (want && p->fn_wide) {
+            e = cudaFuncSetAttribute((const void*)p->fn_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::wide::SMEM_BYTES);
+            if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(wide, smem=%d): %s", pinn::wide::SMEM_BYTES, cudaGetErrorString(e)); }
+            e = cudaFuncGetAttributes(&fa, (const void*)p->fn_wide);
+            if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes(wide): %s", cudaGetErrorString(e)); }
+            p->wide = true; p->gmem = true; p->threads = pinn::wide::NT; p->n_wacc = 0;
+            p->smem_bytes = pinn::wide::SMEM_BYTES; p->regs = fa.numRegs;
+        }
+    }
+
     *out = p;
     return PINN_OK;
 }
@@ -267,7 +326,8 @@ extern "C" size_t pinn_workspace_bytes(const PinnPlan* p, int64_t n_points) {
     if (!p) return 0;
     size_t b = ws_spill_off(p);
     size_t spill = 0;
-    if (p->gmem) spill = (size_t)p->sm_count * (p->threads / 32) * p->h.rows_total * RS * sizeof(float);
+    if (p->wide) spill = (size_t)p->sm_count * pinn::wide::spill_floats_per_cta(p->h.n_layers, 1 + p->h.nf + p->h.ns) * sizeof(float);
+    else if (p->gmem) spill = (size_t)p->sm_count * (p->threads / 32) * p->h.rows_total * RS * sizeof(float);
     if (p->fwd_gmem) {
         size_t f = (size_t)p->sm_count * (p->fwd_threads / 32) * p->fwd_rows * RS * sizeof(float);
         if (f > spill) spill = f;
@@ -364,6 +424,109 @@ extern "C" int pinn_comm_destroy(PinnComm* c) {
     return PINN_OK;
 }
 
+extern "C" int pinn_comm_status(PinnComm* c, int* aborted, int reset) {
+    if (!c || !aborted) return fail(PINN_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned int word = 0;
+    CUDA_TRY(cudaMemcpy(&word, c->local + 4, 4, cudaMemcpyDeviceToHost));
+    *aborted = (int)word;
+    if (reset && word) { word = 0; CUDA_TRY(cudaMemcpy(c->local + 4, &word, 4, cudaMemcpyHostToDevice)); }
+    return PINN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host-batch pipeline (see the header): staging buffers, copy / read-back streams, events.
+// ---------------------------------------------------------------------------------------------------
+#define PINN_PIPE_MAX_STAGE 8
+struct PinnPipe {
+    int device, n_stage;
+    size_t bytes;                                  // one staging buffer
+    float* buf[PINN_PIPE_MAX_STAGE];
+    cudaEvent_t copied[PINN_PIPE_MAX_STAGE];       // H2D into buf[k] has completed
+    cudaEvent_t freed[PINN_PIPE_MAX_STAGE];        // the compute stream no longer reads buf[k]
+    cudaStream_t copy_stream, d2h_stream;
+};
+
+extern "C" int pinn_pipe_destroy(PinnPipe* q) {
+    if (!q) return PINN_OK;
+    cudaSetDevice(q->device);
+    if (q->copy_stream) cudaStreamSynchronize(q->copy_stream);
+    if (q->d2h_stream) cudaStreamSynchronize(q->d2h_stream);
+    for (int k = 0; k < q->n_stage; ++k) {
+        if (q->buf[k]) cudaFree(q->buf[k]);
+        if (q->copied[k]) cudaEventDestroy(q->copied[k]);
+        if (q->freed[k]) cudaEventDestroy(q->freed[k]);
+    }
+    if (q->copy_stream) cudaStreamDestroy(q->copy_stream);
+    if (q->d2h_stream) cudaStreamDestroy(q->d2h_stream);
+    delete q;
+    return PINN_OK;
+}
+
+extern "C" int pinn_pipe_create(const PinnPlan* p, int n_stage, int64_t local_n, PinnPipe** out) {
+    if (!p || !out) return fail(PINN_E_INVALID, "null argument");
+    if (n_stage < 1 || n_stage > PINN_PIPE_MAX_STAGE || local_n <= 0)
+        return fail(PINN_E_INVALID, "pinn_pipe_create: n_stage %d (1..%d), local_n %lld", n_stage, PINN_PIPE_MAX_STAGE, (long long)local_n);
+    PinnPipe* q = new (std::nothrow) PinnPipe();
+    if (!q) return fail(PINN_E_INVALID, "out of memory");
+    memset(q, 0, sizeof(*q));
+    q->device = p->device; q->n_stage = n_stage;
+    q->bytes = (size_t)local_n * p->h.total * sizeof(float);
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&q->d2h_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < n_stage && e == cudaSuccess; ++k) {
+        e = cudaMalloc(&q->buf[k], q->bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&q->copied[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&q->freed[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { pinn_pipe_destroy(q); return fail(PINN_E_CUDA, "pinn_pipe_create: %s", cudaGetErrorString(e)); }
+    *out = q;
+    return PINN_OK;
+}
+
+extern "C" float* pinn_pipe_buffer(PinnPipe* q, int slot) {
+    return (q && slot >= 0 && slot < q->n_stage) ? q->buf[slot] : nullptr;
+}
+
+extern "C" int pinn_pipe_finish(PinnPipe* q, int slot, const float* ring_src, float* loss_dst, void* stream) {
+    if (!q || slot < 0 || slot >= q->n_stage) return fail(PINN_E_INVALID, "pinn_pipe_finish: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaEventRecord(q->freed[slot], st));
+    if (ring_src && loss_dst) {
+        // the step's loss travels on its own stream so that the read-back never sits between two steps
+        CUDA_TRY(cudaStreamWaitEvent(q->d2h_stream, q->freed[slot], 0));
+        CUDA_TRY(cudaMemcpyAsync(loss_dst, ring_src, sizeof(float), cudaMemcpyDeviceToHost, q->d2h_stream));
+    }
+    return PINN_OK;
+}
+
+extern "C" int pinn_pipe_step(PinnPipe* q, int slot, const float* host_points, void* graph_exec,
+                              const float* ring_src, float* loss_dst, void* stream) {
+    if (!q || slot < 0 || slot >= q->n_stage || !host_points) return fail(PINN_E_INVALID, "pinn_pipe_step: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaStreamWaitEvent(q->copy_stream, q->freed[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(q->buf[slot], host_points, q->bytes, cudaMemcpyHostToDevice, q->copy_stream));
+    CUDA_TRY(cudaEventRecord(q->copied[slot], q->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, q->copied[slot], 0));
+    if (!graph_exec) return PINN_OK;
+    CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)graph_exec, st));
+    return pinn_pipe_finish(q, slot, ring_src, loss_dst, stream);
+}
+
+extern "C" int pinn_pipe_wait(PinnPipe* q, int slot) {
+    if (!q || slot < 0 || slot >= q->n_stage) return fail(PINN_E_INVALID, "pinn_pipe_wait: bad argument");
+    CUDA_TRY(cudaEventSynchronize(q->copied[slot]));
+    return PINN_OK;
+}
+
+extern "C" int pinn_pipe_sync(PinnPipe* q) {
+    if (!q) return fail(PINN_E_INVALID, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(q->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(q->d2h_stream));
+    return PINN_OK;
+}
+
 static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* params, const float* points,
                      const PinnColumn* cols, uint64_t seed, const uint64_t* step_counter, uint64_t step_value,
                      uint64_t point_offset, int64_t n_points, float inv_global_n, float* grads_and_loss,
@@ -389,9 +552,24 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
     a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_partials_off());
     a.spill = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_spill_off(p));
     a.n_wacc = p->n_wacc; a.rows_total = p->h.rows_total;
+    static long long comm_timeout = 0;
+    if (!comm_timeout) {
+        const char* e = getenv("PINN_COMM_TIMEOUT_S");
+        double sec = e ? atof(e) : 60.0;
+        if (!(sec > 0.0)) sec = 60.0;
+        comm_timeout = (long long)(sec * 1.9e9);          // SM clock ticks (clock64), ~1.9 GHz
+    }
+    a.comm_timeout = comm_timeout;
     a.comm_rank = comm ? comm->rank : 0;
     a.comm_world = comm ? comm->world : 0;
     for (int r = 0; r < PINN_COMM_MAX_RANKS; ++r) a.comm_peers[r] = comm ? comm->peers[r] : nullptr;
+    if (p->wide) {
+        long long tiles = (n_points + pinn::wide::T - 1) / pinn::wide::T;
+        const int grid = (int)(tiles < p->sm_count ? tiles : p->sm_count);
+        p->fn_wide<<<grid, pinn::wide::NT, pinn::wide::SMEM_BYTES, st>>>(plan, a);
+        CUDA_TRY(cudaGetLastError());
+        return PINN_OK;
+    }
     const int grid = grid_for(p, n_points, p->threads);
     StepKernelFn fn = p->gmem ? p->fn_gmem : p->fn_smem;
     fn<<<grid, p->threads, p->smem_bytes, st>>>(plan, a);
@@ -471,6 +649,7 @@ extern "C" int pinn_plan_info(const PinnPlan* p, PinnPlanInfo* info) {
     info->nf = p->h.nf; info->ns = p->h.ns; info->channels = C;
     info->threads_per_cta = p->threads; info->ctas_per_sm = 1;
     info->activations_in_smem = p->gmem ? 0 : 1;
+    info->tensor_core = p->wide ? 1 : 0;
     info->smem_bytes = p->smem_bytes; info->regs_per_thread = p->regs; info->sm_count = p->sm_count;
     info->rows_per_point = p->h.rows_total;
     info->flops_per_point = 6ll * C * macs;

@@ -34,6 +34,7 @@ struct StepArgs {
     // in-kernel all-reduce over NVLink peer memory (comm_world == 0: off)
     char* comm_peers[PINN_COMM_MAX_RANKS]; // exchange buffer of every rank, mapped through CUDA IPC
     int comm_rank, comm_world;
+    long long comm_timeout;                // clock64 ticks a rank waits for its peers before poisoning the step
 };
 
 // Layout of one rank's exchange buffer (pinn_comm_create): epoch counter, arrival flags, slots.
@@ -154,6 +155,97 @@ __device__ __forceinline__ void stage_weights(float* smem, const SmemLayout& SL,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Grid tail shared by every step kernel: the CTA has written its partial [n_out_floats] to
+// a.partials[blockIdx.x]; the last CTA to arrive (ticket) folds all partials in block order and — in
+// data-parallel runs — exchanges the folded vector with the peers over NVLink.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_floats) {
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    if (tid == 0) {
+        unsigned int t = atomicAdd(a.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // --- data-parallel runs: the all-reduce of [grads | loss] happens right here, over NVLink peer
+        // memory.  This rank's folded vector is stored into its slot in EVERY rank's exchange buffer, an
+        // arrival flag follows (release, system scope), and once all flags of this epoch are in, every
+        // rank sums the slots in rank order — identical bits everywhere, no second kernel, no NCCL call.
+        // Slots and flags are double-buffered by epoch parity: a rank can be at most one step ahead.
+        __shared__ unsigned int s_epoch;
+        __shared__ int s_timeout;
+        if (tid == 0) s_timeout = 0;
+        float* slot_base = nullptr;
+        unsigned int epoch = 0;
+        int par = 0;
+        const size_t slot_f = comm_slot_floats(n_out_floats);
+        if (a.comm_world > 1) {
+            if (tid == 0) {
+                unsigned int* ep = reinterpret_cast<unsigned int*>(a.comm_peers[a.comm_rank]);
+                s_epoch = *ep + 1u;
+                *ep = s_epoch;
+            }
+            __syncthreads();
+            epoch = s_epoch;
+            par = (int)(epoch & 1u);
+            slot_base = reinterpret_cast<float*>(a.comm_peers[a.comm_rank] + PINN_COMM_SLOTS_OFF);
+        }
+        for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            int b = 0;
+            const float* src = a.partials + i;
+            for (; b + 3 < (int)gridDim.x; b += 4) {
+                s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
+                s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
+                s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
+                s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
+            }
+            for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
+            const float total = (s0 + s1) + (s2 + s3);
+            if (a.comm_world > 1) {
+                for (int r = 0; r < a.comm_world; ++r) {       // peer stores over NVLink
+                    float* dst = reinterpret_cast<float*>(a.comm_peers[r] + PINN_COMM_SLOTS_OFF) +
+                                 ((size_t)par * a.comm_world + a.comm_rank) * slot_f;
+                    dst[i] = total;
+                }
+            } else {
+                a.out[i] = total;
+            }
+        }
+        if (a.comm_world > 1) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < a.comm_world) {
+                unsigned int* flag = reinterpret_cast<unsigned int*>(a.comm_peers[tid] + PINN_COMM_FLAGS_OFF) +
+                                     par * PINN_COMM_MAX_RANKS + a.comm_rank;
+                st_release_sys(flag, epoch);
+                const unsigned int* mine_f = reinterpret_cast<const unsigned int*>(a.comm_peers[a.comm_rank] + PINN_COMM_FLAGS_OFF) +
+                                             par * PINN_COMM_MAX_RANKS + tid;
+                // a peer that never arrives (crashed rank) must not hang the GPU: give up after the time limit, and make
+                // that sticky (word 1 of the local buffer) so that the remaining steps fail fast
+                volatile unsigned int* aborted = reinterpret_cast<volatile unsigned int*>(a.comm_peers[a.comm_rank]) + 1;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(mine_f) != epoch) {
+                    if (*aborted || clock64() - t0 > a.comm_timeout) { *aborted = 1u; s_timeout = 1; break; }
+                }
+            }
+            __syncthreads();
+            const float* slots = slot_base + (size_t)par * a.comm_world * slot_f;
+            for (int i = tid; i < n_out_floats; i += blockDim.x) {
+                float s = 0.0f;
+                for (int r = 0; r < a.comm_world; ++r) s += __ldcv(slots + (size_t)r * slot_f + i);
+                a.out[i] = s_timeout ? __int_as_float(0x7fc00000) : s;      // poison instead of hanging
+            }
+        }
+        if (tid == 0) *a.ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // The fit-step kernel.
 // ---------------------------------------------------------------------------------------------------
 template <int NF, int NS, bool GMEM, int MAXT, int JF, bool GEN>
@@ -231,88 +323,7 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
         for (int w = 0; w < a.n_wacc; ++w) s += wacc_all[w * n_out_floats + i];
         mine[i] = s;
     }
-    __threadfence();
-    __syncthreads();
-    __shared__ unsigned int s_last;
-    if (tid == 0) {
-        unsigned int t = atomicAdd(a.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        // --- data-parallel runs: the all-reduce of [grads | loss] happens right here, over NVLink peer
-        // memory.  This rank's folded vector is stored into its slot in EVERY rank's exchange buffer, an
-        // arrival flag follows (release, system scope), and once all flags of this epoch are in, every
-        // rank sums the slots in rank order — identical bits everywhere, no second kernel, no NCCL call.
-        // Slots and flags are double-buffered by epoch parity: a rank can be at most one step ahead.
-        __shared__ unsigned int s_epoch;
-        __shared__ int s_timeout;
-        if (tid == 0) s_timeout = 0;
-        float* slot_base = nullptr;
-        unsigned int epoch = 0;
-        int par = 0;
-        const size_t slot_f = comm_slot_floats(n_out_floats);
-        if (a.comm_world > 1) {
-            if (tid == 0) {
-                unsigned int* ep = reinterpret_cast<unsigned int*>(a.comm_peers[a.comm_rank]);
-                s_epoch = *ep + 1u;
-                *ep = s_epoch;
-            }
-            __syncthreads();
-            epoch = s_epoch;
-            par = (int)(epoch & 1u);
-            slot_base = reinterpret_cast<float*>(a.comm_peers[a.comm_rank] + PINN_COMM_SLOTS_OFF);
-        }
-        for (int i = tid; i < n_out_floats; i += blockDim.x) {
-            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-            int b = 0;
-            const float* src = a.partials + i;
-            for (; b + 3 < (int)gridDim.x; b += 4) {
-                s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
-                s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
-                s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
-                s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
-            }
-            for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
-            const float total = (s0 + s1) + (s2 + s3);
-            if (a.comm_world > 1) {
-                for (int r = 0; r < a.comm_world; ++r) {       // peer stores over NVLink
-                    float* dst = reinterpret_cast<float*>(a.comm_peers[r] + PINN_COMM_SLOTS_OFF) +
-                                 ((size_t)par * a.comm_world + a.comm_rank) * slot_f;
-                    dst[i] = total;
-                }
-            } else {
-                a.out[i] = total;
-            }
-        }
-        if (a.comm_world > 1) {
-            __threadfence_system();
-            __syncthreads();
-            if (tid < a.comm_world) {
-                unsigned int* flag = reinterpret_cast<unsigned int*>(a.comm_peers[tid] + PINN_COMM_FLAGS_OFF) +
-                                     par * PINN_COMM_MAX_RANKS + a.comm_rank;
-                st_release_sys(flag, epoch);
-                const unsigned int* mine_f = reinterpret_cast<const unsigned int*>(a.comm_peers[a.comm_rank] + PINN_COMM_FLAGS_OFF) +
-                                             par * PINN_COMM_MAX_RANKS + tid;
-                // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~4 s, and make
-                // that sticky (word 1 of the local buffer) so that the remaining steps fail fast
-                volatile unsigned int* aborted = reinterpret_cast<volatile unsigned int*>(a.comm_peers[a.comm_rank]) + 1;
-                const long long t0 = clock64();
-                while (ld_acquire_sys(mine_f) != epoch) {
-                    if (*aborted || clock64() - t0 > 8000000000ll) { *aborted = 1u; s_timeout = 1; break; }
-                }
-            }
-            __syncthreads();
-            const float* slots = slot_base + (size_t)par * a.comm_world * slot_f;
-            for (int i = tid; i < n_out_floats; i += blockDim.x) {
-                float s = 0.0f;
-                for (int r = 0; r < a.comm_world; ++r) s += __ldcv(slots + (size_t)r * slot_f + i);
-                a.out[i] = s_timeout ? __int_as_float(0x7fc00000) : s;      // poison instead of hanging
-            }
-        }
-        if (tid == 0) *a.ticket = 0u;
-    }
+    finish_grid(a, n_out_floats);
 }
 
 

@@ -1,0 +1,11 @@
+// wide_step_kernel (tcgen05 / TMEM tile kernel for wide networks) instantiations for NF = 0 first-order directions
+#include "pinn_wide_kernel.cuh"
+
+pinn::StepKernelFn pinn_wide_variant_nf0(int ns) {
+    using namespace pinn::wide;
+    switch (ns) {
+        case 0: return wide_step_kernel<0, 0>;
+
+        default: return nullptr;
+    }
+}

@@ -1,0 +1,11 @@
+// wide_step_kernel (tcgen05 / TMEM tile kernel for wide networks) instantiations for NF = 1 first-order directions
+#include "pinn_wide_kernel.cuh"
+
+pinn::StepKernelFn pinn_wide_variant_nf1(int ns) {
+    using namespace pinn::wide;
+    switch (ns) {
+        case 0: return wide_step_kernel<1, 0>;
+        case 1: return wide_step_kernel<1, 1>;
+        default: return nullptr;
+    }
+}

@@ -1,0 +1,14 @@
+// wide_step_kernel (tcgen05 / TMEM tile kernel for wide networks) instantiations for NF = 4 first-order directions
+#include "pinn_wide_kernel.cuh"
+
+pinn::StepKernelFn pinn_wide_variant_nf4(int ns) {
+    using namespace pinn::wide;
+    switch (ns) {
+        case 0: return wide_step_kernel<4, 0>;
+        case 1: return wide_step_kernel<4, 1>;
+        case 2: return wide_step_kernel<4, 2>;
+        case 3: return wide_step_kernel<4, 3>;
+        case 4: return wide_step_kernel<4, 4>;
+        default: return nullptr;
+    }
+}

@@ -20,7 +20,8 @@ import torch
 from . import _native
 
 _GRAPH_MIN_ITERS = 8
-_HOST_GRAPH_MIN_ITERS = 64          # host-sampler mode: one capture per staging buffer
+_HOST_GRAPH_MIN_ITERS = 8           # host-sampler mode: one capture per staging buffer
+_RING_LEN = 1 << 15                 # device loss ring (steps between two read-backs of a long fit)
 
 
 def _dist():
@@ -120,7 +121,10 @@ class FusedEngine:
         ws_bytes = self.lib.pinn_workspace_bytes(self.plan, 1)
         self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ring = torch.zeros(_RING_LEN, dtype=torch.float32, device=self.device)
         self.steps_done = 0
+        self._graphs, self._pipes, self._pinned_batches = {}, {}, {}
+        self._opt_obj, self._opt_key, self._loss_host = None, None, None
         self.seed = solver.seed
 
         self.comm = None
@@ -158,6 +162,7 @@ class FusedEngine:
 
     def __del__(self):
         try:
+            self._drop_graphs()
             if getattr(self, 'comm', None):
                 self.lib.pinn_comm_destroy(self.comm)
                 self.comm = None
@@ -258,12 +263,51 @@ class FusedEngine:
         return u
 
     # ------------------------------------------------------------------------------------------
+    def _optimizer_for(self, optimizer, lr, kwargs):
+        """ The optimizer of this fit.  The reference builds a NEW optimizer on every `fit` (model_torch.py:419-422);
+        a fresh fused Adam differs from a used one only by its state, so when the request repeats the previous one
+        exactly, the existing object is kept and its state is zeroed in place — which keeps the captured CUDA graphs
+        (they hold pointers into that state) valid across `fit` calls.  Returns (optimizer, state_is_materialised). """
+        solver = self.solver
+        if optimizer is None:
+            solver._make_optimizer(None, lr)
+            return solver.optimizer, bool(solver.optimizer.state)
+        params = [p for p in solver.model.parameters() if p.requires_grad]
+        key = (optimizer, float(lr), tuple(sorted((k, repr(v)) for k, v in kwargs.items())), tuple(id(p) for p in params))
+        prev = solver.optimizer
+        if (prev is not None and prev is self._opt_obj and key == self._opt_key and optimizer in ('Adam', 'AdamW')
+                and prev.state and not any(kwargs.get(k) for k in ('amsgrad', 'maximize'))):
+            with torch.no_grad():
+                for st in prev.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            return prev, True
+        self._drop_graphs()
+        solver._make_optimizer(optimizer, lr, fused_hint=True, **kwargs)
+        self._opt_obj, self._opt_key = solver.optimizer, key
+        return solver.optimizer, False
+
+    def _drop_graphs(self):
+        self._graphs = {}
+        for pipe in getattr(self, '_pipes', {}).values():
+            self.lib.pinn_pipe_destroy(pipe)
+        self._pipes = {}
+
+    def _pinned_losses(self, n):
+        if self._loss_host is None or self._loss_host.numel() < n:
+            self._loss_host = torch.zeros(max(n, 4096), dtype=torch.float32).pin_memory()
+        return self._loss_host
+
     def fit(self, niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs):
         solver = self.solver
-        solver._make_optimizer(optimizer, lr, fused_hint=True, **kwargs)
-        opt = solver.optimizer
+        opt, opt_ready = self._optimizer_for(optimizer, lr, kwargs)
+        if solver.optimizer is not self._opt_obj:          # optimizer=None with an optimizer built elsewhere
+            self._drop_graphs()
+            self._opt_obj, self._opt_key = solver.optimizer, None
         nums = solver._constraint_numbers(loss_terms)
         fused_constraints = [e for e in (self._constraint_plan(n) for n in nums) if e is not None]
+        fused_nums = tuple(n for n in nums if self._constraint_plan(n) is not None)
         nums = [n for n in nums if self._constraint_plan(n) is None]     # the rest is added by autograd
         dist = _dist()
         world = dist.get_world_size() if dist is not None else 1
@@ -273,137 +317,209 @@ class FusedEngine:
             raise ValueError('batch_size %d is smaller than the number of ranks %d' % (batch_size, world))
         inv_n = 1.0 / float(batch_size)
         total = solver.model.total
+        if niters <= 0:
+            return
 
         # every parameter's .grad must be the view of `out` (a previous zero_grad may have dropped it)
         for p, o in self.entries:
             if p.grad is None or p.grad.data_ptr() != self.out.data_ptr() + 4 * o:
                 p.grad = self.out[o:o + p.numel()].view(p.shape)
+        # parameters that came to life after the engine was built (a V() first met inside a constraint that does not
+        # lower) own their .grad: the kernel never overwrites it, so it has to be cleared every step like the
+        # reference does (model_torch.py:428)
+        entry_ids = {id(p) for p, _ in self.entries}
+        stray_params = [p for p in solver.model.parameters() if id(p) not in entry_ids]
 
-        cols, host_sampler = None, None
+        if dist is not None:
+            # ranks may reach this fit seconds apart (rank 0 plotting or saving between fits): the in-kernel
+            # all-reduce waits only a bounded time for its peers, so line the ranks up first
+            dist.barrier()
+
+        cols, host_sampler, cols_key = None, None, None
         if sampler is not None:
             dev_cols = sampler.device_columns() if hasattr(sampler, 'device_columns') else None
             if dev_cols is not None and len(dev_cols) == total and os.environ.get('PYDENS_B200_HOST_SAMPLER') != '1':
                 try:
                     cols = _native.make_columns(dev_cols, total)
+                    cols_key = bytes(cols)
                 except ValueError:                    # more mixture components than the kernel takes
                     cols = None
             if cols is None:
                 host_sampler = sampler
         solver.model.train()
 
-        ring = torch.zeros(max(niters, 1), dtype=torch.float32, device=self.device)
+        ring, ring_len = self.ring, self.ring.numel()
         start = self.steps_done
         loss_idx = self.n_params
-        zero_host = None
+        stream = self._stream()
+        ring_ptr = ring.data_ptr()
+        vals = np.empty(niters, dtype=np.float32)
+        drained = [0]
 
-        if host_sampler is not None:
-            # staging depth = how many steps the host may run ahead of the GPU (absorbs host jitter; matters most
-            # with several ranks, where the in-kernel all-reduce makes every rank wait for the slowest host)
-            n_stage = max(2, int(os.environ.get('PYDENS_B200_STAGES', '4')))
-            pinned = [torch.empty((batch_size, total), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
-            events = [torch.cuda.Event() for _ in range(n_stage)]          # H2D of buffer k has completed
-            free_ev = [torch.cuda.Event() for _ in range(n_stage)]         # compute no longer reads dev_pts[k]
-            copy_stream = torch.cuda.Stream(device=self.device)
-            d2h_stream = torch.cuda.Stream(device=self.device)
-            dev_pts = [torch.empty((local_n, total), dtype=torch.float32, device=self.device) for _ in range(n_stage)]
-            zero_host = torch.zeros(max(niters, 1), dtype=torch.float32).pin_memory()
+        def drain(upto):
+            """ losses of steps [drained, upto) of this fit: device ring -> vals (the ring has been synchronised) """
+            if upto > drained[0]:
+                idx = (start + np.arange(drained[0], upto)) % ring_len
+                vals[drained[0]:upto] = ring.cpu().numpy()[idx]
+                drained[0] = upto
 
-        def one_step(i, points=None):
+        def one_step(points=None, full_points=None):
             self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
             if dist is not None and self.comm is None:
                 dist.all_reduce(self.out)              # no peer-memory path: NCCL sums [grads | loss]
             for entry in fused_constraints:            # after the all-reduce: every rank adds the same term
                 self._constraint_step(entry)
             if nums:
-                xs = solver._sample_host(sampler if host_sampler is not None else None, batch_size) \
-                    if points is None else [points[:, k:k + 1] for k in range(total)]
+                # constraints that stay on autograd see the step's own batch — the WHOLE global batch, identical
+                # on every rank (so that every replica adds the same gradient) and with requires_grad set, as the
+                # reference hands them to the constraint (model_torch.py:436, :451-457)
+                if full_points is not None:
+                    batch = full_points
+                else:                                  # in-kernel sampler: replay the batch the kernel just drew
+                    batch = self.sample(batch_size, cols, point_offset=0)
+                xs = [batch[:, k:k + 1].clone().requires_grad_() for k in range(total)]
+                for p in stray_params:
+                    p.grad = None
                 closs = solver._constraint_loss(nums, xs, criterion)
                 closs.backward()
                 self.out[loss_idx] += closs.detach()
             opt.step()
             _native.check(self.lib.pinn_record_loss(self.plan, C.c_void_p(self.out.data_ptr()),
-                                                    C.c_void_p(ring.data_ptr()), C.c_int64(ring.numel()),
+                                                    C.c_void_p(ring_ptr), C.c_int64(ring_len),
                                                     C.c_void_p(self.step_counter.data_ptr()), self._stream()))
 
         capturable = bool(opt.param_groups and opt.param_groups[0].get('capturable', False))
-        use_graph = (host_sampler is None and not nums and capturable and niters >= _GRAPH_MIN_ITERS
-                     and os.environ.get('PYDENS_B200_NO_GRAPH') != '1')
+        graphs_ok = capturable and not nums and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'
+        from .solver import _progress
         done = 0
-        if use_graph:
-            one_step(0)                               # real step 0: also materialises optimizer state
-            done = 1
-            # several steps per graph when there are many: one replay = G optimizer steps, which matters in
-            # the launch-bound small-batch regime (README example: batch 100 x 1500 iterations)
-            per_graph = int(os.environ.get('PYDENS_B200_GRAPH_STEPS', '0')) or (4 if niters - 1 >= 64 else 1)
-            graph = None
-            try:
-                torch.cuda.synchronize(self.device)
 
-                def body():
-                    for k in range(per_graph):
-                        one_step(1 + k)
-                graph = capture_graph(self.device, body)
-            except Exception:                         # capture unsupported here: plain launches
-                graph = None
-                torch.cuda.synchronize(self.device)
+        if host_sampler is None:
+            # ---------------- points sampled in the kernel: replay graphs of `per_graph` steps ----------------
+            per_graph = int(os.environ.get('PYDENS_B200_GRAPH_STEPS', '0')) or (4 if niters >= 64 else 1)
+            key = ('dev', batch_size, local_n, cols_key, fused_nums, per_graph)
+            graph = self._graphs.get(key) if graphs_ok else None
+            if graphs_ok and graph is None and niters >= _GRAPH_MIN_ITERS:
+                if not opt_ready:
+                    one_step()                        # real step 0: also materialises optimizer state
+                    done = 1
+                try:
+                    torch.cuda.synchronize(self.device)
+
+                    def body():
+                        for _ in range(per_graph):
+                            one_step()
+                    # capture executes nothing, but a first launch of a freshly captured kernel sequence must not
+                    # be preceded by a dry run: the capture itself is side-effect free
+                    graph = capture_graph(self.device, body)
+                    self._graphs[key] = graph
+                except Exception:                     # capture unsupported here: plain launches
+                    graph = None
+                    torch.cuda.synchronize(self.device)
             if graph is not None:
-                for _ in range((niters - 1) // per_graph):
+                n_rep = (niters - done) // per_graph
+                budget = ring_len - done
+                for _ in range(n_rep):
+                    if budget < per_graph:            # the ring is about to wrap: read it out first
+                        torch.cuda.synchronize(self.device)
+                        drain(done)
+                        budget = ring_len
                     graph.replay()
-                done = 1 + ((niters - 1) // per_graph) * per_graph
-                del graph
-        if done < niters:
-            from .solver import _progress
-            stage_graphs = None
-            for i in _progress(niters - done):
-                if host_sampler is not None:
-                    k = i % len(pinned)
-                    events[k].synchronize()
-                    batch = host_sampler.sample(batch_size)
-                    if isinstance(batch, torch.Tensor):
-                        src = batch if batch.dtype == torch.float32 else batch.float()
-                    else:
-                        pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)))
-                        src = pinned[k]
-                    # the batch travels on its own stream so that the copy of step i+1 overlaps step i
-                    cur = torch.cuda.current_stream(self.device)
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(free_ev[k])
-                        dev_pts[k].copy_(src[point_offset:point_offset + local_n], non_blocking=True)
-                        events[k].record(copy_stream)
-                    cur.wait_event(events[k])
-                    if stage_graphs is not None:
-                        stage_graphs[k].replay()
-                    else:
-                        one_step(done + i, dev_pts[k])
-                    free_ev[k].record(cur)
-                    # the step's loss goes to the host every step (as in the reference, :464) — from the device
-                    # ring and on its own stream, so that the read-back never sits between two steps
-                    with torch.cuda.stream(d2h_stream):
-                        d2h_stream.wait_event(free_ev[k])
-                        r = (start + done + i) % ring.numel()
-                        zero_host[done + i:done + i + 1].copy_(ring[r:r + 1], non_blocking=True)
-                    # after the first (eager) step the optimizer state exists: capture the compute part of the
-                    # step once per staging buffer, so that every later step is copy -> replay -> loss read
-                    if (i == 0 and stage_graphs is None and capturable and not nums and niters - done >= _HOST_GRAPH_MIN_ITERS
-                            and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'):
-                        try:
-                            torch.cuda.synchronize(self.device)
-                            graphs = []
-                            for kk in range(len(pinned)):
-                                graphs.append(capture_graph(self.device, lambda kk=kk: one_step(0, dev_pts[kk]),
-                                                            pool=graphs[0].pool() if graphs else None))
-                            stage_graphs = graphs
-                        except Exception:               # capture unsupported here: keep plain launches
-                            stage_graphs = None
-                            torch.cuda.synchronize(self.device)
-                else:
-                    one_step(done + i)
-            stage_graphs = None
-        self.steps_done = start + niters
-        torch.cuda.synchronize(self.device)
-        if host_sampler is not None:
-            vals = zero_host.numpy().copy()
+                    done += per_graph
+                    budget -= per_graph
+            for _ in _progress(niters - done):
+                if done - drained[0] >= ring_len:
+                    torch.cuda.synchronize(self.device)
+                    drain(done)
+                one_step()
+                done += 1
+            self.steps_done = start + niters
+            torch.cuda.synchronize(self.device)
+            drain(niters)
         else:
-            idx = (start + np.arange(niters)) % max(niters, 1)
-            vals = ring.cpu().numpy()[idx]
+            # ---------------- host batches: native pipeline, one call per step ----------------
+            # staging depth = how many steps the host may run ahead of the GPU (absorbs host jitter; matters most
+            # with several ranks, where the in-kernel all-reduce makes every rank wait for the slowest host)
+            n_stage = max(2, min(8, int(os.environ.get('PYDENS_B200_STAGES', '4'))))
+            pkey = (local_n, n_stage)
+            pipe = self._pipes.get(pkey)
+            if pipe is None:
+                pipe = C.c_void_p()
+                _native.check(self.lib.pinn_pipe_create(self.plan, n_stage, C.c_int64(local_n), C.byref(pipe)))
+                self._pipes[pkey] = pipe
+            bufs = [_RawPtr(self.lib.pinn_pipe_buffer(pipe, k)) for k in range(n_stage)]
+            pinned = self._pinned_batches.get((batch_size, n_stage))
+            loss_host = self._pinned_losses(niters)
+            loss_ptr = loss_host.data_ptr()
+            key = ('host', batch_size, local_n, n_stage, fused_nums)
+            execs = self._graphs.get(key) if graphs_ok else None
+            exec_ptrs = [g.raw_cuda_graph_exec() for g in execs] if execs else None
+            keep = [None] * n_stage                    # the tensors whose memory a copy in flight still reads
+            off_bytes = point_offset * total * 4
+            want_graphs = graphs_ok and execs is None and niters >= _HOST_GRAPH_MIN_ITERS
+
+            for i in _progress(niters):
+                k = i % n_stage
+                batch = host_sampler.sample(batch_size)
+                if isinstance(batch, torch.Tensor) and batch.dtype == torch.float32 and batch.is_contiguous() \
+                        and batch.device.type == 'cpu':
+                    src = batch                        # copied from where it lies (pinned or not)
+                else:
+                    if pinned is None:
+                        pinned = [torch.empty((batch_size, total), dtype=torch.float32).pin_memory()
+                                  for _ in range(n_stage)]
+                        self._pinned_batches[(batch_size, n_stage)] = pinned
+                    _native.check(self.lib.pinn_pipe_wait(pipe, k))          # its previous copy has left the buffer
+                    if isinstance(batch, torch.Tensor):
+                        pinned[k].copy_(batch.detach().to('cpu', torch.float32).reshape(batch_size, total))
+                    else:
+                        pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)).reshape(batch_size, total))
+                    src = pinned[k]
+                keep[k] = src
+                r = (start + i) % ring_len
+                if exec_ptrs is not None:
+                    _native.check(self.lib.pinn_pipe_step(pipe, k, C.c_void_p(src.data_ptr() + off_bytes),
+                                                          C.c_void_p(exec_ptrs[k]), C.c_void_p(ring_ptr + 4 * r),
+                                                          C.c_void_p(loss_ptr + 4 * i), stream))
+                    continue
+                _native.check(self.lib.pinn_pipe_step(pipe, k, C.c_void_p(src.data_ptr() + off_bytes), None, None, None, stream))
+                full = None
+                if nums:
+                    full = src.to(self.device, non_blocking=True)
+                    if dist is not None:
+                        dist.broadcast(full, 0)
+                one_step(bufs[k], full)
+                _native.check(self.lib.pinn_pipe_finish(pipe, k, C.c_void_p(ring_ptr + 4 * r), C.c_void_p(loss_ptr + 4 * i), stream))
+                # after the first (eager) step the optimizer state exists: capture the compute part of the step
+                # once per staging buffer, so that every later step is ONE native call (copy -> graph -> loss read)
+                if want_graphs:
+                    want_graphs = False
+                    try:
+                        torch.cuda.synchronize(self.device)
+                        graphs = []
+                        for kk in range(n_stage):
+                            graphs.append(capture_graph(self.device, lambda kk=kk: one_step(bufs[kk]),
+                                                        pool=graphs[0].pool() if graphs else None))
+                        self._graphs[key] = graphs
+                        exec_ptrs = [g.raw_cuda_graph_exec() for g in graphs]
+                    except Exception:               # capture unsupported here: keep plain launches
+                        exec_ptrs = None
+                        torch.cuda.synchronize(self.device)
+            self.steps_done = start + niters
+            torch.cuda.synchronize(self.device)
+            vals[:] = loss_host[:niters].numpy()
+        if self.comm is not None:
+            aborted = C.c_int(0)
+            _native.check(self.lib.pinn_comm_status(self.comm, C.byref(aborted), 1))
+            if aborted.value:
+                raise RuntimeError('pydens_b200: a rank did not reach the in-kernel all-reduce within the time limit '
+                                   '(PINN_COMM_TIMEOUT_S); the gradients of this fit were poisoned with NaN')
         solver.losses.extend(np.array(v, dtype=np.float32) for v in vals[:niters])
+
+
+class _RawPtr:
+    """ A device pointer with the one method `_step` needs from a tensor. """
+    def __init__(self, ptr):
+        self.ptr = int(ptr)
+
+    def data_ptr(self):
+        return self.ptr

@@ -142,6 +142,12 @@ class Solver:
         except tracer.NotLowerable as exc:
             self._traced = None
             self._lower_error = str(exc)
+        except Exception as exc:                          # noqa: BLE001
+            # anything else the symbolic proxies choke on (a TypeError from an operator they do not define, an
+            # IndexError from user code that indexes its argument ...): the reference accepts such equations, so
+            # under backend='auto' they simply stay on autograd; backend='fused' reports the reason
+            self._traced = None
+            self._lower_error = '%s while tracing: %s' % (type(exc).__name__, exc)
 
     def _tracing_run(self, fn, *args):
         def call():
@@ -183,6 +189,13 @@ class Solver:
                 # the library understood the request but its kernels do not cover it (e.g. a network whose
                 # weights do not fit shared memory): that is a lowering failure, not a crash
                 if exc.code == _native.E_UNSUPPORTED and self.backend == 'auto':
+                    self._traced, self._lower_error = None, str(exc)
+                    return None
+                raise
+            except _native.LibraryMissing as exc:
+                # fresh clone without build(): backend='auto' keeps working on autograd (loudly, fit() warns with
+                # this reason); backend='fused' must fail
+                if self.backend == 'auto':
                     self._traced, self._lower_error = None, str(exc)
                     return None
                 raise

@@ -419,7 +419,17 @@ class Sym:
     def _compare(self, other):
         raise NotLowerable('comparisons (data-dependent control flow) in a traced callable')
 
-    __lt__ = __le__ = __gt__ = __ge__ = _compare
+    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _compare
+    __hash__ = object.__hash__                 # defining __eq__ would otherwise make Sym unhashable
+
+    # what a tensor would accept but a symbolic column cannot express: bail out of the fused path cleanly
+    # (the reference runs such equations on autograd, model_torch.py:448) instead of raising a TypeError
+    def _unsupported(self, *args, **kwargs):
+        raise NotLowerable('indexing / integer arithmetic / len() on a traced tensor')
+
+    __getitem__ = __setitem__ = __mod__ = __rmod__ = __floordiv__ = __rfloordiv__ = _unsupported
+    __len__ = __iter__ = __matmul__ = __rmatmul__ = __and__ = __or__ = __xor__ = __invert__ = _unsupported
+    __int__ = __float__ = __index__ = _unsupported
 
     def __getattr__(self, name):
         if name.startswith('__'):

@@ -167,7 +167,8 @@ GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param':
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
                'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01),
-               'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01)}
+               'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01),
+               'wave3d': (12, 96, 0.001)}
 
 
 def make_points(name, batch, seed):
