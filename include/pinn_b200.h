@@ -101,6 +101,9 @@ typedef struct PinnInstr {
 #define PINN_COL_NORMAL     1   /* a + b * N(0,1)          */
 #define PINN_COL_CONST      2   /* a                       */
 #define PINN_COL_MIXTURE    3   /* one of n_comp simple columns, drawn per point (batchflow `s1 | s2`) */
+#define PINN_COL_TNORMAL    4   /* a + b * N(0,1) conditioned on comp_a[0] <= value <= comp_b[0]: batchflow
+                                   `NumpySampler('n', ...).truncate(high, low)` by rejection — up to 16 re-draws on
+                                   further Philox blocks, then the value is clamped into the interval           */
 #define PINN_MAX_MIX        4
 
 /* A mixture column picks component i with probability cum_w[i] - cum_w[i-1] (cum_w[n_comp-1] == 1) and then
@@ -306,6 +309,27 @@ int pinn_pipe_step(PinnPipe* pipe, int slot, const float* host_points, void* gra
 int pinn_pipe_finish(PinnPipe* pipe, int slot, const float* ring_src, float* loss_dst, void* stream);
 int pinn_pipe_wait(PinnPipe* pipe, int slot);
 int pinn_pipe_sync(PinnPipe* pipe);
+
+/*
+ * `k_steps` WHOLE optimizer steps in one launch — the body of the reference loop including optimizer.step()
+ * (model_torch.py:427-464) — for the small-batch regime where a step is launch-latency bound (README.md:36-53:
+ * batch_size=100, niters=1500).  One CTA keeps the parameters, both Adam moments and the gradient in shared memory
+ * between the steps.  Adam follows torch.optim.Adam (no amsgrad):  m <- lerp(m, g, 1-beta1),
+ * v <- beta2 v + (1-beta2) g^2,  p <- p - lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps),  t = opt_step0 + 1 ...
+ *
+ *   params, exp_avg, exp_avg_sq   [n_params] in/out;   mask [n_params]: 1 = trainable, 0 = frozen (left untouched)
+ *   step_tensors                  the optimizer's per-tensor step counters (fp32 scalars laid out contiguously), += k_steps
+ *   points                        [k_steps, n_points, ndims+nparams] explicit batches, or NULL (+ cols) to sample in-kernel
+ *   step_counter                  device step number: Philox counter word and ring index, as in pinn_step; += k_steps
+ *   losses_ring[(step) % ring_len] receives the loss of every step.
+ * pinn_multi_step_max_points: largest batch the kernel takes (0: this network does not fit the kernel).
+ */
+int pinn_multi_step_max_points(const PinnPlan* plan);
+int pinn_multi_step(const PinnPlan* plan, float* params, float* exp_avg, float* exp_avg_sq, const float* mask,
+                    float* step_tensors, int n_step_tensors, const float* points, const PinnColumn* cols,
+                    uint64_t seed, uint64_t* step_counter, int64_t n_points, int k_steps,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, float opt_step0,
+                    float* losses_ring, int64_t ring_len, void* stream);
 
 /* Forward only: u = ansatz(net(x)) for explicit points — the work of Solver.predict
  * (model_torch.py:466-487) and of the `_forward` closure handed to constraints (:451-454).

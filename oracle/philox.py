@@ -72,6 +72,25 @@ def sample(cols, total, seed, step, point_offset, n):
         z = rad * np.cos(np.float32(6.283185307179586) * u2)
         return (np.float64(b32) * z.astype(np.float64) + np.float64(a32)).astype(np.float32)
 
+    def tnormal(k, a, b, lo, hi):
+        # restatement of sample_tnormal (pinn_device.cuh): candidates from words (0,1) / (2,3) of block 2+k with the
+        # attempt number in bits 8..15 of the block word; first hit wins; after 16 misses the clamped mean
+        a32, b32, lo32, hi32 = np.float32(a), np.float32(b), np.float32(lo), np.float32(hi)
+        res = np.full(n, np.minimum(np.maximum(a32, lo32), hi32), dtype=np.float32)
+        todo = np.ones(n, dtype=bool)
+        for att in range(8):
+            w = philox4x32_10(c0, c1, c2, np.full(n, c3base | np.uint32(att << 8) | np.uint32(2 + k), dtype=np.uint32), k0, k1)
+            for half in range(2):
+                w1, w2 = (w[2], w[3]) if half else (w[0], w[1])
+                u1 = ((w1 >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * scale
+                u2 = (w2 >> np.uint32(8)).astype(np.float32) * scale
+                z = np.sqrt(np.float32(-2.0) * np.log(u1)) * np.cos(np.float32(6.283185307179586) * u2)
+                v = (np.float64(b32) * z.astype(np.float64) + np.float64(a32)).astype(np.float32)
+                hit = todo & (v >= lo32) & (v <= hi32)
+                res[hit] = v[hit]
+                todo &= ~hit
+        return res
+
     groups = {}
     for k, col in enumerate(cols):
         if col[0] == 'mix':                        # ('mix', group key, [(weight, kind, a, b), ...])
@@ -87,6 +106,8 @@ def sample(cols, total, seed, step, point_offset, n):
                 idx += (u >= cum[c]).astype(np.int64)
             vals = np.stack([simple(k, kind, a, b) for _, kind, a, b in comps], axis=0)
             out[:, k] = vals[idx, np.arange(n)]
+        elif len(col) == 5:                        # (4, loc, scale, low, high): truncated normal
+            out[:, k] = tnormal(k, *col[1:])
         else:
             out[:, k] = simple(k, *col)
     return out

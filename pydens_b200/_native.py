@@ -10,7 +10,7 @@ ABI_VERSION = 9
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
-COL_UNIFORM, COL_NORMAL, COL_CONST, COL_MIXTURE = 0, 1, 2, 3
+COL_UNIFORM, COL_NORMAL, COL_CONST, COL_MIXTURE, COL_TNORMAL = 0, 1, 2, 3, 4
 MAX_MIX = 4
 
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN, E_WORKSPACE = -1, -2, -3, -4, -5
@@ -74,7 +74,8 @@ EXPORTS = ('pinn_last_error', 'pinn_abi_version', 'pinn_plan_create', 'pinn_plan
            'pinn_workspace_bytes', 'pinn_out_floats', 'pinn_step', 'pinn_forward', 'pinn_sample',
            'pinn_record_loss', 'pinn_plan_info', 'pinn_comm_create', 'pinn_comm_connect', 'pinn_comm_destroy',
            'pinn_step_allreduce', 'pinn_comm_status', 'pinn_pipe_create', 'pinn_pipe_destroy', 'pinn_pipe_buffer',
-           'pinn_pipe_step', 'pinn_pipe_finish', 'pinn_pipe_wait', 'pinn_pipe_sync')
+           'pinn_pipe_step', 'pinn_pipe_finish', 'pinn_pipe_wait', 'pinn_pipe_sync', 'pinn_multi_step',
+           'pinn_multi_step_max_points')
 
 LIB_PATH = os.environ.get('PYDENS_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpinn_b200.so')
 _lib = None
@@ -126,6 +127,11 @@ def load():
     lib.pinn_pipe_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pinn_pipe_wait.argtypes = [C.c_void_p, C.c_int]
     lib.pinn_pipe_sync.argtypes = [C.c_void_p]
+    lib.pinn_multi_step_max_points.argtypes = [C.c_void_p]
+    lib.pinn_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.POINTER(PinnColumn), C.c_uint64, C.c_void_p, C.c_int64, C.c_int,
+                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_int64, C.c_void_p]
     lib.pinn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p]
     lib.pinn_sample.argtypes = [C.c_void_p, C.POINTER(PinnColumn), C.c_uint64, C.c_void_p, C.c_uint64,
@@ -166,6 +172,9 @@ def make_columns(cols, total):
                 acc += float(w)
                 arr[i].cum_w[j] = 1.0 if j == len(comps) - 1 else acc / total_w
                 arr[i].comp_kind[j], arr[i].comp_a[j], arr[i].comp_b[j] = int(kind), float(a), float(b)
+        elif len(col) == 5:                               # (COL_TNORMAL, loc, scale, low, high)
+            arr[i].kind, arr[i].a, arr[i].b = col[:3]
+            arr[i].comp_a[0], arr[i].comp_b[0] = float(col[3]), float(col[4])
         else:
             arr[i].kind, arr[i].a, arr[i].b = col
     return arr

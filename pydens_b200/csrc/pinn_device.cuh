@@ -160,8 +160,29 @@ PINN_HD float sample_simple(int kind, float a, float b, int k, uint64_t gidx, ui
     return fmaf(b, z, a);
 }
 
+// Truncated normal by rejection (batchflow `.truncate(high, low)` on a normal column): candidate t comes from words
+// (0,1) / (2,3) of Philox block 2+k with the attempt number t/2 in bits 8..15 of the block word; the first candidate
+// inside [lo, hi] wins; after 16 misses the mean is clamped into the interval (mass outside 16 sigma-ish only).
+PINN_HD float sample_tnormal(float a, float b, float lo, float hi, int k, uint64_t gidx, uint64_t step, uint64_t seed) {
+    for (int att = 0; att < 8; ++att) {
+        const uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16) | (uint32_t)(att << 8) | (uint32_t)(2 + k);
+        const Philox4 p = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t w1 = half ? p.z : p.x, w2 = half ? p.w : p.y;
+            const float u1 = ((float)(w1 >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0,1]
+            const float u2 = u01_from_bits(w2);
+            const float z = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+            const float v = fmaf(b, z, a);
+            if (v >= lo && v <= hi) return v;
+        }
+    }
+    return fminf(fmaxf(a, lo), hi);
+}
+
 PINN_HD float sample_column(const PinnColumn& col, int k, uint64_t gidx, uint64_t step, uint64_t seed,
                             const Philox4& blk0, const Philox4& blk1) {
+    if (col.kind == PINN_COL_TNORMAL) return sample_tnormal(col.a, col.b, col.comp_a[0], col.comp_b[0], k, gidx, step, seed);
     if (col.kind != PINN_COL_MIXTURE) return sample_simple(col.kind, col.a, col.b, k, gidx, step, seed, blk0, blk1);
     uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16) | (uint32_t)(10 + col.group);
     Philox4 p = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,

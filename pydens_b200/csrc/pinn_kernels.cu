@@ -24,11 +24,11 @@
 #include "pinn_host_plan.h"
 
 // wide_step_kernel instantiations live in pinn_wide_nf*.cu
-pinn::StepKernelFn pinn_wide_variant_nf0(int ns);
-pinn::StepKernelFn pinn_wide_variant_nf1(int ns);
-pinn::StepKernelFn pinn_wide_variant_nf2(int ns);
-pinn::StepKernelFn pinn_wide_variant_nf3(int ns);
-pinn::StepKernelFn pinn_wide_variant_nf4(int ns);
+pinn::StepKernelFn pinn_wide_variant_nf0(int ns, int threads);
+pinn::StepKernelFn pinn_wide_variant_nf1(int ns, int threads);
+pinn::StepKernelFn pinn_wide_variant_nf2(int ns, int threads);
+pinn::StepKernelFn pinn_wide_variant_nf3(int ns, int threads);
+pinn::StepKernelFn pinn_wide_variant_nf4(int ns, int threads);
 
 namespace pinn {
 
@@ -122,20 +122,20 @@ static bool find_variant(int nf, int ns, Variant& out) {
     }
     if (!a || !b) return false;
     out = *a;
-    out.smem_gen_fn = b->smem_gen_fn; out.gmem_gen_fn = b->gmem_gen_fn;
+    out.smem_gen_fn = b->smem_gen_fn; out.gmem_gen_fn = b->gmem_gen_fn; out.multi_fn = b->multi_fn;
     return true;
 }
 
 // The tensor-core tile kernel (pinn_wide_kernel.cuh) covers plain dense chains with polynomial-family activations
 // and hidden widths <= 64; it pays off once the layers are wide enough to be real GEMMs.
-static pinn::StepKernelFn find_wide_variant(int nf, int ns) {
+static pinn::StepKernelFn find_wide_variant(int nf, int ns, int threads) {
     if (ns < 0 || ns > nf) return nullptr;
     switch (nf) {
-        case 0: return pinn_wide_variant_nf0(ns);
-        case 1: return pinn_wide_variant_nf1(ns);
-        case 2: return pinn_wide_variant_nf2(ns);
-        case 3: return pinn_wide_variant_nf3(ns);
-        case 4: return pinn_wide_variant_nf4(ns);
+        case 0: return pinn_wide_variant_nf0(ns, threads);
+        case 1: return pinn_wide_variant_nf1(ns, threads);
+        case 2: return pinn_wide_variant_nf2(ns, threads);
+        case 3: return pinn_wide_variant_nf3(ns, threads);
+        case 4: return pinn_wide_variant_nf4(ns, threads);
     }
     return nullptr;
 }
@@ -158,6 +158,8 @@ struct PinnPlan {
     int device;
     bool wide;                               // the tcgen05 tile kernel runs the step
     StepKernelFn fn_wide;
+    MultiKernelFn fn_multi;                  // persistent multi-step kernel, or nullptr when it does not fit
+    int multi_threads, multi_nwacc, multi_smem;
     Variant var_store;
     const Variant* var;
     StepKernelFn fn_smem, fn_gmem;           // the pair matching this plan (plain or general)
@@ -274,6 +276,34 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); }
     }
 
+    // ---- persistent multi-step kernel (small batches): per-point state + parameters + Adam moments in shared memory ----
+    {
+        p->fn_multi = nullptr; p->multi_threads = 0; p->multi_nwacc = 0; p->multi_smem = 0;
+        if (var->multi_fn) {
+            cudaFuncAttributes fm;
+            e = cudaFuncGetAttributes(&fm, (const void*)var->multi_fn);
+            if (e == cudaSuccess) {
+                int mw = var->maxt / 32;
+                if (65536 / (fm.numRegs * 32) < mw) mw = 65536 / (fm.numRegs * 32);
+                const int extra = 3 * align4(h.n_params) + align4(n_out_floats);
+                const int mbudget = p->smem_optin - (int)fm.sharedSizeBytes - 64;
+                for (int nw = mw; nw >= 1 && !p->fn_multi; --nw) {
+                    SmemLayout SL = smem_layout(h.weights_floats, n_out_floats, nw,
+                                                h.rows_total * RS * nw > h.n_params ? h.rows_total * RS * nw : h.n_params);
+                    if ((SL.total_f + extra) * 4 <= mbudget) {
+                        p->fn_multi = var->multi_fn; p->multi_threads = nw * 32; p->multi_nwacc = nw;
+                        p->multi_smem = (SL.total_f + extra) * 4;
+                    }
+                }
+                if (p->fn_multi) {
+                    e = allow_max_smem((const void*)p->fn_multi, p->smem_optin);
+                    if (e != cudaSuccess) p->fn_multi = nullptr;
+                }
+            }
+            (void)cudaGetLastError();
+        }
+    }
+
     // ---- wide networks: the tensor-core tile kernel takes the step (PINN_FORCE_KERNEL=thread|wide overrides) ----
     {
         p->wide = false; p->fn_wide = nullptr;
@@ -286,13 +316,15 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
             if (!eligible) { delete p; return fail(PINN_E_UNSUPPORTED, "PINN_FORCE_KERNEL=wide: this network is outside what the tile kernel covers"); }
             want = true;
         }
-        if (want) p->fn_wide = find_wide_variant(s->nf, s->ns);
+        int wide_threads = 256;                     // PINN_WIDE_THREADS=512: four threads per point (experiments)
+        { const char* wt = getenv("PINN_WIDE_THREADS"); if (wt && atoi(wt) == 512) wide_threads = 512; }
+        if (want) p->fn_wide = find_wide_variant(s->nf, s->ns, wide_threads);
         if (want && p->fn_wide) {
             e = cudaFuncSetAttribute((const void*)p->fn_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::wide::SMEM_BYTES);
             if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncSetAttribute(wide, smem=%d): %s", pinn::wide::SMEM_BYTES, cudaGetErrorString(e)); }
             e = cudaFuncGetAttributes(&fa, (const void*)p->fn_wide);
             if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes(wide): %s", cudaGetErrorString(e)); }
-            p->wide = true; p->gmem = true; p->threads = pinn::wide::NT; p->n_wacc = 0;
+            p->wide = true; p->gmem = true; p->threads = wide_threads; p->n_wacc = 0;
             p->smem_bytes = pinn::wide::SMEM_BYTES; p->regs = fa.numRegs;
         }
     }
@@ -345,7 +377,9 @@ static int resolve_cols(const PinnPlan* p, const PinnColumn* cols, PinnColumn* o
         if (cols && i < p->h.total) out[i] = cols[i];
         else { out[i].kind = PINN_COL_UNIFORM; out[i].a = 0.0f; out[i].b = 1.0f; }
         const PinnColumn& c = out[i];
-        if (c.kind < 0 || c.kind > PINN_COL_MIXTURE) return fail(PINN_E_INVALID, "column %d kind %d", i, c.kind);
+        if (c.kind < 0 || c.kind > PINN_COL_TNORMAL) return fail(PINN_E_INVALID, "column %d kind %d", i, c.kind);
+        if (c.kind == PINN_COL_TNORMAL && !(c.comp_a[0] <= c.comp_b[0]))
+            return fail(PINN_E_INVALID, "column %d: truncated normal with low %g > high %g", i, c.comp_a[0], c.comp_b[0]);
         if (c.kind == PINN_COL_MIXTURE) {
             if (c.n_comp < 2 || c.n_comp > PINN_MAX_MIX || c.group < 0 || c.group >= PINN_MAX_DIMS)
                 return fail(PINN_E_INVALID, "column %d: mixture of %d components in group %d", i, c.n_comp, c.group);
@@ -566,7 +600,7 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
     if (p->wide) {
         long long tiles = (n_points + pinn::wide::T - 1) / pinn::wide::T;
         const int grid = (int)(tiles < p->sm_count ? tiles : p->sm_count);
-        p->fn_wide<<<grid, pinn::wide::NT, pinn::wide::SMEM_BYTES, st>>>(plan, a);
+        p->fn_wide<<<grid, p->threads, pinn::wide::SMEM_BYTES, st>>>(plan, a);
         CUDA_TRY(cudaGetLastError());
         return PINN_OK;
     }
@@ -593,6 +627,38 @@ extern "C" int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm, c
     if (!comm) return fail(PINN_E_INVALID, "null communicator");
     return step_impl(plan, comm, params, points, cols, seed, step_counter, step_value, point_offset, n_points,
                      inv_global_n, grads_and_loss, residual_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pinn_multi_step_max_points(const PinnPlan* p) {
+    // one CTA walks the batch tile by tile: any batch works, but the kernel is meant for the launch-bound regime
+    return (p && p->fn_multi) ? 4096 : 0;
+}
+
+extern "C" int pinn_multi_step(const PinnPlan* cp, float* params, float* exp_avg, float* exp_avg_sq, const float* mask,
+                               float* step_tensors, int n_step_tensors, const float* points, const PinnColumn* cols,
+                               uint64_t seed, uint64_t* step_counter, int64_t n_points, int k_steps,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, float opt_step0,
+                               float* losses_ring, int64_t ring_len, void* stream) {
+    PinnPlan* p = const_cast<PinnPlan*>(cp);
+    if (!p || !params || !exp_avg || !exp_avg_sq || !mask || !step_counter || !losses_ring)
+        return fail(PINN_E_INVALID, "null argument");
+    if (!p->fn_multi) return fail(PINN_E_UNSUPPORTED, "the persistent multi-step kernel does not fit this network in shared memory");
+    if (n_points <= 0 || n_points > pinn_multi_step_max_points(p) || k_steps <= 0 || ring_len <= 0 || n_step_tensors < 0)
+        return fail(PINN_E_INVALID, "pinn_multi_step: n_points %lld (1..%d), k_steps %d", (long long)n_points, pinn_multi_step_max_points(p), k_steps);
+    if (!aligned16(params)) return fail(PINN_E_ALIGN, "params must be 16-byte aligned");
+    DevPlan plan = p->h;
+    if (!points) { int rc = resolve_cols(p, cols, plan.cols); if (rc) return rc; }
+    MultiArgs a;
+    a.params = params; a.exp_avg = exp_avg; a.exp_avg_sq = exp_avg_sq; a.mask = mask;
+    a.step_tensors = step_tensors; a.n_step_tensors = n_step_tensors; a.points = points; a.seed = seed;
+    a.step_counter = reinterpret_cast<unsigned long long*>(step_counter);
+    a.n_points = n_points; a.inv_n = 1.0f / (float)n_points; a.k_steps = k_steps;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.opt_step0 = opt_step0;
+    a.losses_ring = losses_ring; a.ring_len = ring_len;
+    a.n_wacc = p->multi_nwacc; a.rows_total = p->h.rows_total;
+    p->fn_multi<<<1, p->multi_threads, p->multi_smem, (cudaStream_t)stream>>>(plan, a);
+    CUDA_TRY(cudaGetLastError());
+    return PINN_OK;
 }
 
 extern "C" int pinn_forward(const PinnPlan* p, const float* params, const float* points, int64_t n_points,

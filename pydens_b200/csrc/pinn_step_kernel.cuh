@@ -159,18 +159,63 @@ __device__ __forceinline__ void stage_weights(float* smem, const SmemLayout& SL,
 // a.partials[blockIdx.x]; the last CTA to arrive (ticket) folds all partials in block order and — in
 // data-parallel runs — exchanges the folded vector with the peers over NVLink.
 // ---------------------------------------------------------------------------------------------------
+constexpr int FOLD_GROUP = 12;           // CTAs per first-level fold group (148 CTAs -> 13 groups)
+
+// sum of `n` partial vectors (stride n_out_floats) at element i, fixed order, four loads in flight
+__device__ __forceinline__ float fold_column(const float* __restrict__ src, int n, int n_out_floats) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int b = 0;
+    for (; b + 3 < n; b += 4) {
+        s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
+        s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
+        s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
+        s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
+    }
+    for (; b < n; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
+    return (s0 + s1) + (s2 + s3);
+}
+
 __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_floats) {
     const int tid = threadIdx.x;
+    // Two-level fold, fixed order: the last CTA of every group of FOLD_GROUP consecutive CTAs sums its group into
+    // the group's first slot; the last GROUP to finish sums the group results.  (One CTA folding all 148 partials
+    // was a 7 us serial tail at cfg2 and > 100 us for a 51 KB gradient vector.)
+    const int n_groups = ((int)gridDim.x + FOLD_GROUP - 1) / FOLD_GROUP;
+    const int group = (int)blockIdx.x / FOLD_GROUP;
+    const int g_first = group * FOLD_GROUP;
+    const int g_size = min(FOLD_GROUP, (int)gridDim.x - g_first);
     __threadfence();
     __syncthreads();
     __shared__ unsigned int s_last;
     if (tid == 0) {
-        unsigned int t = atomicAdd(a.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+        unsigned int t = atomicAdd(a.ticket + 1 + group, 1u);
+        s_last = (t == (unsigned int)g_size - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last) {
+    if (!s_last) return;
+    __threadfence();
+    if (n_groups > 1) {
+        float* gdst = a.partials + (size_t)g_first * n_out_floats;
+        for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            const float t = fold_column(a.partials + (size_t)g_first * n_out_floats + i, g_size, n_out_floats);
+            gdst[i] = t;                                 // this thread read every partial's element i before writing it
+        }
         __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            a.ticket[1 + group] = 0u;
+            unsigned int t = atomicAdd(a.ticket, 1u);
+            s_last = (t == (unsigned int)n_groups - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    } else if (tid == 0) {
+        a.ticket[1] = 0u;
+    }
+    const int n_fold = (n_groups > 1) ? n_groups : g_size;
+    const size_t fold_stride = (n_groups > 1) ? (size_t)FOLD_GROUP * n_out_floats : (size_t)n_out_floats;
+    {
         // --- data-parallel runs: the all-reduce of [grads | loss] happens right here, over NVLink peer
         // memory.  This rank's folded vector is stored into its slot in EVERY rank's exchange buffer, an
         // arrival flag follows (release, system scope), and once all flags of this epoch are in, every
@@ -195,16 +240,17 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
             slot_base = reinterpret_cast<float*>(a.comm_peers[a.comm_rank] + PINN_COMM_SLOTS_OFF);
         }
         for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            // partial vectors to fold: the group results (stride FOLD_GROUP slots), or the CTAs of the only group
             float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
             int b = 0;
             const float* src = a.partials + i;
-            for (; b + 3 < (int)gridDim.x; b += 4) {
-                s0 += __ldcg(src + (size_t)(b + 0) * n_out_floats);
-                s1 += __ldcg(src + (size_t)(b + 1) * n_out_floats);
-                s2 += __ldcg(src + (size_t)(b + 2) * n_out_floats);
-                s3 += __ldcg(src + (size_t)(b + 3) * n_out_floats);
+            for (; b + 3 < n_fold; b += 4) {
+                s0 += __ldcg(src + (size_t)(b + 0) * fold_stride);
+                s1 += __ldcg(src + (size_t)(b + 1) * fold_stride);
+                s2 += __ldcg(src + (size_t)(b + 2) * fold_stride);
+                s3 += __ldcg(src + (size_t)(b + 3) * fold_stride);
             }
-            for (; b < (int)gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * n_out_floats);
+            for (; b < n_fold; ++b) s0 += __ldcg(src + (size_t)b * fold_stride);
             const float total = (s0 + s1) + (s2 + s3);
             if (a.comm_world > 1) {
                 for (int r = 0; r < a.comm_world; ++r) {       // peer stores over NVLink
@@ -327,12 +373,156 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
 }
 
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent multi-step kernel for the small-batch regime (README example: batch 100 x 1500 iterations,
+// reference loop pydens/model_torch.py:426-464 INCLUDING optimizer.step() :461): ONE CTA runs `k_steps`
+// whole optimizer steps per launch.  Parameters, Adam moments and the gradient live in shared memory
+// between the steps; every step is  sample / read points -> forward jets -> residual -> reverse ->
+// CTA-wide fixed-order reduction -> Adam (torch.optim.Adam semantics, fused/capturable form) -> re-layout
+// of the weights, with no launch and no trip to global memory in between.  Opt-in:
+// Solver.fit(..., steps_per_launch=k).
+// ---------------------------------------------------------------------------------------------------
+struct MultiArgs {
+    float* params;                 // [n_params] in/out
+    float* exp_avg;                // [n_params] in/out (Adam first moment)
+    float* exp_avg_sq;             // [n_params] in/out (Adam second moment)
+    const float* mask;             // [n_params] 1 = trainable (requires_grad), 0 = frozen
+    float* step_tensors;           // [n_step_tensors] the optimizer's per-parameter step counters (float), += k_steps
+    int n_step_tensors;
+    const float* points;           // [k_steps][n_points][total] explicit batches, or nullptr: sample in-kernel
+    uint64_t seed;
+    unsigned long long* step_counter;   // device step number (Philox counter word, ring index); += k_steps
+    long long n_points;
+    float inv_n;
+    int k_steps;
+    float lr, beta1, beta2, eps, weight_decay;
+    float opt_step0;               // optimizer steps taken before this launch
+    float* losses_ring;
+    long long ring_len;
+    int n_wacc, rows_total;
+};
+
+template <int NF, int NS, int MAXT, int JF>
+__global__ void __launch_bounds__(MAXT, 1) multi_step_kernel(const __grid_constant__ DevPlan P, const MultiArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int n_out_floats = P.n_params + 4;
+    const int storage_f = max(P.n_params, a.rows_total * RS * nwarps);
+    const SmemLayout SL = smem_layout(P.weights_floats, n_out_floats, a.n_wacc, storage_f);
+    // behind the single-step layout: flat parameters, both Adam moments, the folded gradient
+    float* flat = smem + SL.total_f;
+    float* mom1 = flat + align4(P.n_params);
+    float* mom2 = mom1 + align4(P.n_params);
+    float* gsum = mom2 + align4(P.n_params);
+    stage_weights(smem, SL, P, a.params);
+    float* sw = smem + SL.weights_f;
+    float* wacc_all = smem + SL.wacc_f;
+    for (int i = tid; i < P.n_params; i += blockDim.x) {
+        flat[i] = a.params[i]; mom1[i] = a.exp_avg[i]; mom2[i] = a.exp_avg_sq[i];
+    }
+    __syncthreads();
+
+    GradSink sink;
+    sink.atomic = (a.n_wacc == 1 && nwarps > 1);
+    sink.wacc = wacc_all + (a.n_wacc == 1 ? 0 : warp * n_out_floats);
+    sink.dump = P.n_params + 2;
+    float* st = smem + SL.storage_f + (size_t)warp * a.rows_total * RS + lane;
+    const unsigned long long step0 = *a.step_counter;
+    const long long n_tiles = (a.n_points + 31) / 32;
+
+    for (int s = 0; s < a.k_steps; ++s) {
+        for (int i = tid; i < n_out_floats * a.n_wacc; i += blockDim.x) wacc_all[i] = 0.0f;
+        __syncthreads();
+        const uint64_t step = step0 + (unsigned long long)s;
+        PointPartials<NF, NS> part;
+        part.loss = 0.0f; part.sbar = 0.0f;
+#pragma unroll
+        for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
+        for (long long tile = warp; tile < n_tiles; tile += nwarps) {
+            const long long pl = tile * 32 + lane;
+            const bool valid = pl < a.n_points;
+            const long long pe = valid ? pl : a.n_points - 1;
+            if (a.points) {
+                const float* src = a.points + ((size_t)s * a.n_points + (size_t)pe) * P.total;
+                for (int k = 0; k < P.total; ++k) st[k * RS] = __ldg(src + k);
+            } else {
+                const uint64_t gidx = (uint64_t)pe;
+                const uint32_t c3 = (uint32_t)(((step >> 32) & 0xffffu) << 16);
+                Philox4 b0 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3,
+                                           (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                Philox4 b1 = b0;
+                if (P.total > 4)
+                    b1 = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)step, c3 | 1u,
+                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                for (int k = 0; k < P.total; ++k) st[k * RS] = sample_column(P.cols[k], k, gidx, step, a.seed, b0, b1);
+            }
+            point_step<NF, NS, JF, true>(P, sw, flat, st, RS, valid, a.inv_n, sink, part);
+        }
+        {
+            float v = warp_sum(part.loss);
+            if (lane == 0) sink.add(P.n_params, v);
+            v = warp_sum(part.sbar);
+            if (lane == 0) sink.add(P.log_scale_off, v);
+#pragma unroll
+            for (int i = 0; i < PINN_MAX_VARS; ++i) {
+                if (i < P.n_vars) {
+                    float t = warp_sum(part.vbar[i]);
+                    if (lane == 0) sink.add(P.var_off[i], t);
+                }
+            }
+        }
+        __syncthreads();
+        // fold the warps in warp order, then Adam on the flat copy
+        const float t_opt = a.opt_step0 + (float)(s + 1);
+        const float bc1 = 1.0f - powf(a.beta1, t_opt);
+        const float bc2_sqrt = sqrtf(1.0f - powf(a.beta2, t_opt));
+        const float step_size = a.lr / bc1;
+        for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            float g = 0.0f;
+            for (int w = 0; w < a.n_wacc; ++w) g += wacc_all[w * n_out_floats + i];
+            gsum[i] = g;
+            if (i < P.n_params && a.mask[i] != 0.0f) {
+                float pv = flat[i];
+                if (a.weight_decay != 0.0f) g = fmaf(a.weight_decay, pv, g);
+                const float m1 = fmaf(1.0f - a.beta1, g - mom1[i], mom1[i]);
+                const float m2 = fmaf(a.beta2, mom2[i], (1.0f - a.beta2) * g * g);
+                const float denom = sqrtf(m2) / bc2_sqrt + a.eps;
+                flat[i] = pv - step_size * m1 / denom;
+                mom1[i] = m1; mom2[i] = m2;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) a.losses_ring[(step0 + (unsigned long long)s) % (unsigned long long)a.ring_len] = gsum[P.n_params];
+        // the new parameters in both weight layouts (what stage_weights does after its TMA copy)
+        for (int l = 0; l < P.n_layers; ++l) {
+            const DevLayer& L = P.layer[l];
+            const int n = L.n_in * L.n_out;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int j = i / L.n_in, k = i - j * L.n_in;
+                const float w = flat[L.w_off + i];
+                sw[L.wt_s + k * L.n_out_p4 + j] = w;
+                sw[L.w_s + j * L.n_in_p8 + k] = w;
+            }
+            for (int j = tid; j < L.n_out; j += blockDim.x) sw[L.b_s + j] = flat[L.b_off + j];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < P.n_params; i += blockDim.x) {
+        a.params[i] = flat[i]; a.exp_avg[i] = mom1[i]; a.exp_avg_sq[i] = mom2[i];
+    }
+    for (int i = tid; i < a.n_step_tensors; i += blockDim.x) a.step_tensors[i] += (float)a.k_steps;
+    if (tid == 0) *a.step_counter = step0 + (unsigned long long)a.k_steps;
+}
+
+typedef void (*MultiKernelFn)(const DevPlan, const MultiArgs);
+
 typedef void (*StepKernelFn)(const DevPlan, const StepArgs);
 
 struct Variant {
     int nf, ns;
     StepKernelFn smem_fn, gmem_fn;           // plain problems (no residual wiring / oblique directions / IC variables)
     StepKernelFn smem_gen_fn, gmem_gen_fn;   // everything
+    MultiKernelFn multi_fn;                  // persistent multi-step kernel (general variant, smem-resident)
     int maxt;
 };
 
@@ -351,7 +541,9 @@ static Variant make_variant() {
     Variant v;
     v.nf = NF; v.ns = NS;
     v.smem_fn = v.gmem_fn = v.smem_gen_fn = v.gmem_gen_fn = nullptr;
+    v.multi_fn = nullptr;
     if (GEN) {
+        v.multi_fn = multi_step_kernel<NF, NS, Cfg::MAXT, Cfg::JF>;
         v.smem_gen_fn = step_kernel<NF, NS, false, Cfg::MAXT, Cfg::JF, GEN>;
         v.gmem_gen_fn = step_kernel<NF, NS, true, Cfg::MAXT, Cfg::JF, GEN>;
     } else {

@@ -125,6 +125,7 @@ class FusedEngine:
         self.steps_done = 0
         self._graphs, self._pipes, self._pinned_batches = {}, {}, {}
         self._opt_obj, self._opt_key, self._loss_host = None, None, None
+        self._adam_flat = None
         self.seed = solver.seed
 
         self.comm = None
@@ -299,9 +300,111 @@ class FusedEngine:
             self._loss_host = torch.zeros(max(n, 4096), dtype=torch.float32).pin_memory()
         return self._loss_host
 
+    def _bind_adam_state(self, opt):
+        """ Make the optimizer's per-parameter Adam state views of three flat buffers (moments in parameter layout,
+        step counters side by side), so that the persistent multi-step kernel and torch's own `opt.step()` update
+        the very same memory.  -> mask of trainable entries. """
+        if self._adam_flat is None:
+            self._adam_flat = (torch.zeros(self.n_params, dtype=torch.float32, device=self.device),
+                               torch.zeros(self.n_params, dtype=torch.float32, device=self.device),
+                               torch.zeros(len(self.entries), dtype=torch.float32, device=self.device),
+                               torch.zeros(self.n_params, dtype=torch.float32, device=self.device))
+        m, v, steps, mask = self._adam_flat
+        in_opt = {id(q) for g in opt.param_groups for q in g['params']}
+        mask.zero_()
+        rebound = False
+        with torch.no_grad():
+            for idx, (p, o) in enumerate(self.entries):
+                n = p.numel()
+                if id(p) not in in_opt:
+                    continue
+                mask[o:o + n] = 1.0
+                st = opt.state.get(p)
+                mv, vv = m[o:o + n].view(p.shape), v[o:o + n].view(p.shape)
+                if st and 'exp_avg' in st:
+                    if st['exp_avg'].data_ptr() == mv.data_ptr():
+                        continue                                    # already bound
+                    mv.copy_(st['exp_avg']); vv.copy_(st['exp_avg_sq']); steps[idx] = float(st['step'])
+                else:
+                    mv.zero_(); vv.zero_(); steps[idx] = 0.0
+                opt.state[p] = {'step': steps[idx], 'exp_avg': mv, 'exp_avg_sq': vv}
+                rebound = True
+        if rebound:
+            self._drop_graphs()                 # captured steps still point at the previous state tensors
+        return mask
+
+    def _fit_persistent(self, niters, batch_size, sampler, opt, k):
+        """ `niters` optimizer steps, `k` per launch of the persistent multi-step kernel (pinn_multi_step):
+        the reference loop model_torch.py:426-464 with optimizer.step() inside the kernel. """
+        solver = self.solver
+        total = solver.model.total
+        g = opt.param_groups[0]
+        mask = self._bind_adam_state(opt)
+        m, v, steps, _ = self._adam_flat
+        opt_step0 = float(steps.max().item())
+        cols, host_sampler = None, None
+        if sampler is not None:
+            dev_cols = sampler.device_columns() if hasattr(sampler, 'device_columns') else None
+            if dev_cols is not None and len(dev_cols) == total and os.environ.get('PYDENS_B200_HOST_SAMPLER') != '1':
+                try:
+                    cols = _native.make_columns(dev_cols, total)
+                except ValueError:
+                    cols = None
+            if cols is None:
+                host_sampler = sampler
+        solver.model.train()
+        ring, ring_len = self.ring, self.ring.numel()
+        start = self.steps_done
+        vals = np.empty(niters, dtype=np.float32)
+        done, drained = 0, 0
+        lr = float(g['lr']) if not torch.is_tensor(g['lr']) else float(g['lr'].item())
+        b1, b2 = g['betas']
+        while done < niters:
+            kk = min(k, niters - done, ring_len)
+            if done + kk - drained > ring_len:
+                torch.cuda.synchronize(self.device)
+                idx = (start + np.arange(drained, done)) % ring_len
+                vals[drained:done] = ring.cpu().numpy()[idx]
+                drained = done
+            pts = None
+            if host_sampler is not None:
+                host = torch.empty((kk, batch_size, total), dtype=torch.float32).pin_memory()
+                for j in range(kk):
+                    b = host_sampler.sample(batch_size)
+                    host[j].copy_(b if isinstance(b, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)))
+                pts = host.to(self.device, non_blocking=True)
+            _native.check(self.lib.pinn_multi_step(
+                self.plan, C.c_void_p(self.flat.data_ptr()), C.c_void_p(m.data_ptr()), C.c_void_p(v.data_ptr()),
+                C.c_void_p(mask.data_ptr()), C.c_void_p(steps.data_ptr()), C.c_int(steps.numel()),
+                C.c_void_p(pts.data_ptr()) if pts is not None else None, cols, C.c_uint64(self.seed),
+                C.c_void_p(self.step_counter.data_ptr()), C.c_int64(batch_size), C.c_int(kk),
+                C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(g['eps']), C.c_float(g['weight_decay']),
+                C.c_float(opt_step0 + done), C.c_void_p(ring.data_ptr()), C.c_int64(ring_len), self._stream()))
+            done += kk
+        self.steps_done = start + niters
+        torch.cuda.synchronize(self.device)
+        idx = (start + np.arange(drained, niters)) % ring_len
+        vals[drained:niters] = ring.cpu().numpy()[idx]
+        solver.losses.extend(np.array(x, dtype=np.float32) for x in vals)
+
     def fit(self, niters, batch_size, sampler, loss_terms, optimizer, criterion, lr, **kwargs):
         solver = self.solver
+        steps_per_launch = int(kwargs.pop('steps_per_launch', 0) or 0)
         opt, opt_ready = self._optimizer_for(optimizer, lr, kwargs)
+        if steps_per_launch > 0 and niters > 0:
+            g = opt.param_groups[0] if opt.param_groups else {}
+            ok = (type(opt) is torch.optim.Adam and len(opt.param_groups) == 1 and not g.get('amsgrad') and not g.get('maximize')
+                  and _dist() is None and not solver._constraint_numbers(loss_terms)
+                  and 0 < batch_size <= self.lib.pinn_multi_step_max_points(self.plan))
+            if ok:
+                if solver.optimizer is not self._opt_obj:
+                    self._drop_graphs()
+                    self._opt_obj, self._opt_key = solver.optimizer, None
+                return self._fit_persistent(niters, batch_size, sampler, opt, steps_per_launch)
+            import warnings
+            warnings.warn('pydens_b200: steps_per_launch ignored (needs Adam, one device, no constraints, a batch of at '
+                          'most %d points and a network that fits the persistent kernel)'
+                          % self.lib.pinn_multi_step_max_points(self.plan), stacklevel=3)
         if solver.optimizer is not self._opt_obj:          # optimizer=None with an optimizer built elsewhere
             self._drop_graphs()
             self._opt_obj, self._opt_key = solver.optimizer, None

@@ -17,7 +17,7 @@ __all__ = ['Sampler', 'NumpySampler', 'ConstantSampler', 'ScipySampler', 'HistoS
 
 _ALIASES = {'u': 'uniform', 'n': 'normal', 'e': 'exponential', 'g': 'gamma', 'be': 'beta', 'ln': 'lognormal',
             'w': 'weibull', 'p': 'poisson', 'b': 'binomial', 'mvn': 'multivariate_normal', 'c': 'choice'}
-COL_UNIFORM, COL_NORMAL, COL_CONST = 0, 1, 2
+COL_UNIFORM, COL_NORMAL, COL_CONST, COL_TNORMAL = 0, 1, 2, 4
 
 
 def _is_number(x):
@@ -168,7 +168,7 @@ class _Arith(Sampler):
         if len(samplers) != 1 or not _is_number(self.left if samplers[0] is self.right else self.right):
             return None
         cols = samplers[0].device_columns()
-        if cols is None or any(col[0] == 'mix' for col in cols):
+        if cols is None or any(col[0] == 'mix' or len(col) != 3 for col in cols):
             return None
         c = float(self.left if samplers[0] is self.right else self.right)
         sampler_first = samplers[0] is self.left
@@ -201,6 +201,48 @@ class _Apply(Sampler):
     def sample(self, size):
         return np.asarray(self.transform(np.asarray(self.base.sample(size), dtype=np.float64))).reshape(size, -1)
 
+    def device_columns(self):
+        """ A transform that turns out to be a per-column affine map (y_k = s_k x_k + t_k: unit changes, shifts,
+        reflections — the usual use of `.apply`) keeps the columns in the uniform / normal / constant family and runs
+        in-kernel.  The callable is opaque, so it is PROBED: affine and column-separable on random points to 1e-12,
+        else the sampler stays on the host. """
+        cols = self.base.device_columns()
+        if cols is None or self.dim != self.base.dim or any(col[0] == 'mix' or len(col) != 3 for col in cols):
+            return None
+        d = self.dim
+        rng = np.random.RandomState(12345)
+        try:
+            f = lambda pts: np.asarray(self.transform(np.asarray(pts, dtype=np.float64)), dtype=np.float64).reshape(len(pts), -1)   # noqa: E731
+            x0 = np.zeros((1, d))                            # probing at the origin keeps exact coefficients exact
+            y0 = f(x0)
+            if y0.shape != (1, d):
+                return None
+            scale = np.zeros(d)
+            for k in range(d):                               # one-column perturbations: slope, and no cross-talk
+                x1 = x0.copy(); x1[0, k] += 1.0
+                dy = f(x1) - y0
+                scale[k] = dy[0, k]
+                if np.abs(np.delete(dy[0], k)).max(initial=0.0) > 1e-12 * max(1.0, np.abs(y0).max()):
+                    return None
+            shift = y0[0] - scale * x0[0]
+            pts = rng.uniform(-3.0, 3.0, size=(64, d))       # affine everywhere we look, batch size does not matter
+            if np.abs(f(pts) - (pts * scale + shift)).max() > 1e-12 * max(1.0, np.abs(pts * scale + shift).max()):
+                return None
+        except Exception:                                    # noqa: BLE001
+            return None
+        out = []
+        for (kind, a, b), sc, sh in zip(cols, scale, shift):
+            if kind == COL_UNIFORM:
+                out.append((COL_UNIFORM, sc * a + sh, sc * b + sh))
+            elif kind == COL_NORMAL:
+                if sc == 0.0:
+                    out.append((COL_CONST, sh + 0.0 * a, 0.0))
+                else:
+                    out.append((COL_NORMAL, sc * a + sh, abs(sc) * b))
+            else:
+                out.append((COL_CONST, sc * a + sh, 0.0))
+        return out
+
 
 class _Truncated(Sampler):
     def __init__(self, base, high, low, expr, prob, max_iters, sample_anyway):
@@ -216,6 +258,38 @@ class _Truncated(Sampler):
         if self.low is not None:
             ok &= np.all(vals >= np.asarray(self.low, dtype=np.float64), axis=1)
         return pts[ok]
+
+    def device_columns(self):
+        """ Box truncation of independent columns (no `expr`) factorises: a truncated uniform column is the uniform
+        on the intersection of the intervals, a truncated normal column is drawn by rejection in the kernel
+        (PINN_COL_TNORMAL), a constant either survives or makes the sampler empty. """
+        if self.expr is not None:
+            return None
+        cols = self.base.device_columns()
+        if cols is None or any(col[0] == 'mix' or len(col) != 3 for col in cols):
+            return None
+        try:
+            hi = np.broadcast_to(np.asarray(np.inf if self.high is None else self.high, dtype=np.float64), (self.dim,))
+            lo = np.broadcast_to(np.asarray(-np.inf if self.low is None else self.low, dtype=np.float64), (self.dim,))
+        except ValueError:
+            return None
+        out = []
+        for (kind, a, b), l, h in zip(cols, lo, hi):
+            if kind == COL_UNIFORM:
+                lo_k, hi_k = max(min(a, b), l), min(max(a, b), h)
+                if not lo_k < hi_k:
+                    return None                              # empty (or degenerate): let the host path report it
+                out.append((COL_UNIFORM, float(lo_k), float(hi_k)))
+            elif kind == COL_NORMAL:
+                if not l < h:
+                    return None
+                big = 3.0e38
+                out.append((COL_TNORMAL, float(a), float(b), float(max(l, -big)), float(min(h, big))))
+            else:
+                if not l <= a <= h:
+                    return None
+                out.append((COL_CONST, float(a), 0.0))
+        return out
 
     def sample(self, size):
         got, have, rounds, pts = [], 0, 0, None

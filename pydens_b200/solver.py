@@ -256,11 +256,15 @@ class Solver:
         loss_terms  'equation' and/or 'constraint_{k}' (reference :382-389).
         optimizer   name from torch.optim; None re-uses the existing optimizer (reference :391-393).
         criterion   default nn.MSELoss(); anything else runs on the autograd path.
-        kwargs      forwarded to the optimizer constructor.
+        kwargs      forwarded to the optimizer constructor, except
+                    steps_per_launch=k  (fused path, small batches): k whole optimizer steps — Adam included — per
+                    launch of a persistent single-CTA kernel; the launch-bound regime of the README example
+                    (batch_size=100, niters=1500) runs several times faster this way.
         """
         loss_terms = loss_terms if isinstance(loss_terms, (tuple, list)) else (loss_terms,)
         ok, why = self._fused_possible(criterion, loss_terms)
         if not ok:
+            kwargs.pop('steps_per_launch', None)            # fused-path option, not an optimizer argument
             if self.backend == 'fused':
                 raise RuntimeError('backend="fused" but the fused path cannot run: %s' % why)
             if self.backend == 'auto' and not self._warned and self.device.type == 'cuda':

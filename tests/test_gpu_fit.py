@@ -229,3 +229,53 @@ def test_limits_eight_columns_and_deep_network():
     g_ref = torch.cat([p.grad.reshape(-1) for lin in ref.model.conv_block.linears for p in (lin.weight, lin.bias)])
     g_our = grads[:g_ref.numel()]
     assert float((g_our - g_ref).norm() / g_ref.norm()) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# persistent multi-step kernel: k whole optimizer steps (Adam included) per launch — Solver.fit(steps_per_launch=k)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,k', [('poisson2d', 8), ('poisson2d', 40), ('ode_param', 5), ('burgers', 7), ('heat1d_icvar', 4)])
+def test_persistent_kernel_follows_the_reference_fit(name, k):
+    """ README regime (batch 100): the loss curve of the in-kernel Adam loop against the reference's own Solver.fit
+    on identical points (golden trajectory), same tolerances as the one-launch-per-step path. """
+    g = load_golden(name)
+    niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
+    solver = make_solver(name, g['params'])
+    batches = [P.make_points(name, batch, seed=1000 + i) for i in range(niters)]
+    solver.fit(niters=niters, batch_size=batch, sampler=Replay(batches), lr=lr, steps_per_launch=k)
+    losses = np.asarray(solver.losses, dtype=np.float64)
+    ref = g['traj_losses'].astype(np.float64)
+    assert losses.shape == ref.shape
+    assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-3
+    assert abs(losses[-1] - ref[-1]) <= 1e-5 * max(1.0, abs(ref[-1]))
+    final = solver.flat_params().cpu().numpy()
+    assert np.linalg.norm(final - g['traj_params']) / np.linalg.norm(g['traj_params']) <= 1e-3
+
+
+def test_persistent_kernel_equals_stepwise_fit_and_keeps_the_optimizer_state():
+    g = load_golden('poisson2d')
+    a = make_solver('poisson2d', g['params'])
+    a.fit(niters=24, batch_size=100, lr=0.005)                           # in-kernel sampler, one launch per step
+    a.fit(niters=12, batch_size=100, optimizer=None)
+    b = make_solver('poisson2d', g['params'])
+    b.fit(niters=24, batch_size=100, lr=0.005, steps_per_launch=10)      # 10 + 10 + 4 steps in three launches
+    b.fit(niters=12, batch_size=100, optimizer=None)                     # torch's Adam continues on the same state
+    la, lb = np.asarray(a.losses, dtype=np.float64), np.asarray(b.losses, dtype=np.float64)
+    assert la.shape == lb.shape == (36,)
+    assert np.max(np.abs(la - lb) / np.maximum(np.abs(la), 1e-6)) <= 1e-3
+    c = make_solver('poisson2d', g['params'])
+    c.fit(niters=24, batch_size=100, lr=0.005)
+    c.fit(niters=12, batch_size=100, optimizer=None, steps_per_launch=6)  # and the other way round
+    lc = np.asarray(c.losses, dtype=np.float64)
+    assert np.max(np.abs(la - lc) / np.maximum(np.abs(la), 1e-6)) <= 1e-3
+
+
+def test_persistent_kernel_respects_frozen_parameters():
+    g = load_golden('heat2d')
+    solver = make_solver('heat2d', g['params'])
+    solver.model.freeze_trainable(variables=['log_scale'])
+    before = float(solver.model.log_scale)
+    w_before = solver.flat_params().cpu().numpy().copy()
+    solver.fit(niters=6, batch_size=64, lr=0.001, steps_per_launch=3)
+    assert float(solver.model.log_scale) == before
+    assert np.abs(solver.flat_params().cpu().numpy() - w_before).max() > 0

@@ -196,3 +196,29 @@ def test_random_column_tables_bit_exact_against_numpy_restatement():
                 assert np.abs(a[:, k] - b[:, k]).max() <= 4e-6 * max(1.0, np.abs(a[:, k]).max()), (case, k)
             else:
                 assert np.array_equal(a[:, k], b[:, k]), (case, k)
+
+
+def test_truncated_and_transformed_samplers_lower_to_kernel_columns():
+    """ batchflow `.truncate(high, low)` / `.apply(affine)` (tutorial cell `NS('u', dim=2) & ...`): box truncation of
+    independent columns and per-column affine maps stay in-kernel; anything else stays on the host. """
+    from pydens_b200 import NumpySampler as NS
+    s = (NS('n', loc=0.5, scale=2.0).truncate(high=1.5, low=-1.0) & NS('u', low=0, high=4).truncate(high=3, low=1)
+         & NS('u').apply(lambda x: 2 * x + 1) & NS('u', dim=2).truncate(high=[0.5, 0.9]))
+    cols = s.device_columns()
+    assert cols == [(4, 0.5, 2.0, -1.0, 1.5), (0, 1.0, 3.0), (0, 1.0, 3.0), (0, 0.0, 0.5), (0, 0.0, 0.9)]
+    assert NS('u', dim=2).apply(lambda x: x[:, ::-1]).device_columns() is None           # mixes columns
+    assert NS('u').apply(np.sin).device_columns() is None                                # not affine
+    assert NS('u', dim=2).truncate(high=1.0, expr=lambda x: x.sum(axis=1)).device_columns() is None
+    assert NS('u', low=0, high=1).truncate(low=2.0).device_columns() is None              # empty box
+    assert (NS('n').truncate(low=0.0) * 3.0).device_columns() is None                    # arithmetic on a truncated column
+    # the device stream of the truncated normal column == its numpy restatement (same rejection sequence) ...
+    tn = [(4, 0.5, 2.0, -1.0, 1.5), (0, 0.0, 1.0), (4, 0.0, 1.0, 0.0, 3e38)]
+    a = E.emul_sample(tn, 3, 99, 3, 2 ** 33, 30000)
+    b = ph.sample(tn, 3, 99, 3, 2 ** 33, 30000)
+    assert np.array_equal(a[:, 1], b[:, 1]) and np.abs(a - b).max() <= 4e-6
+    assert a[:, 0].min() >= -1.0 and a[:, 0].max() <= 1.5 and a[:, 2].min() >= 0.0
+    # ... and follows the truncated distribution the host sampler draws from
+    host = NS('n', loc=0.5, scale=2.0, seed=3).truncate(high=1.5, low=-1.0).sample(30000)[:, 0]
+    assert abs(a[:, 0].mean() - host.mean()) < 0.03 and abs(a[:, 0].std() - host.std()) < 0.03
+    half = a[:, 2]                                            # half-normal: mean sqrt(2/pi)
+    assert abs(half.mean() - np.sqrt(2 / np.pi)) < 0.02
