@@ -310,14 +310,17 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         int mw = 0;
         const char* fk = getenv("PINN_FORCE_KERNEL");
         const bool eligible = wide_eligible(h, &mw);
-        bool want = eligible && mw >= 24 && (1 + s->nf + s->ns) >= 3;
+        // measured on B200: the tile kernel wins from 64-wide layers with many jet channels on (cfg5: 13.6 ms vs
+        // 15.3 ms); for 30-40-wide networks the CUDA-core kernel is several times faster (cfg4: 2.6 ms vs 9.3 ms) —
+        // per (unit, channel) operand handling costs as much as a 64-long FMA row
+        bool want = eligible && mw >= 48 && (1 + s->nf + s->ns) >= 5;
         if (fk && !strcmp(fk, "thread")) want = false;
         if (fk && !strcmp(fk, "wide")) {
             if (!eligible) { delete p; return fail(PINN_E_UNSUPPORTED, "PINN_FORCE_KERNEL=wide: this network is outside what the tile kernel covers"); }
             want = true;
         }
-        int wide_threads = 256;                     // PINN_WIDE_THREADS=512: four threads per point (experiments)
-        { const char* wt = getenv("PINN_WIDE_THREADS"); if (wt && atoi(wt) == 512) wide_threads = 512; }
+        int wide_threads = 512;                     // four threads per point; PINN_WIDE_THREADS=256: two (experiments)
+        { const char* wt = getenv("PINN_WIDE_THREADS"); if (wt && atoi(wt) == 256) wide_threads = 256; }
         if (want) p->fn_wide = find_wide_variant(s->nf, s->ns, wide_threads);
         if (want && p->fn_wide) {
             e = cudaFuncSetAttribute((const void*)p->fn_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::wide::SMEM_BYTES);

@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
             acc_sbar += ansatz_adjoint<NF, NS>(P, as, ub, Nb);
             acc_bout += Nb[0];
         }
+        auto nb_of = [&](int c) { return Nb[c]; };
         // hand Nb to the other threads of the point (the exchange area is free here)
         __syncthreads();
         if (kh == 0) {
@@ -583,9 +584,11 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
                     post_group(H, g, k0, kc, a0h[q], ax, ay);
                     const int cy = group_y(g);
 #pragma unroll
+                    const float nbx = nb_of(g), nby = cy >= 0 ? nb_of(cy) : 0.0f;
+#pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        t[i] = fmaf(Nb[g], ax[i], t[i]);
-                        if (cy >= 0) t[i] = fmaf(Nb[cy], ay[i], t[i]);
+                        t[i] = fmaf(nbx, ax[i], t[i]);
+                        if (cy >= 0) t[i] = fmaf(nby, ay[i], t[i]);
                     }
                 }
                 put_G(S_GA_HI, S_GA_LO, k0, t);
@@ -618,8 +621,9 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
             // adjoint of the post-activation jet channel c of level h, units k0..k0+7
             auto ld_ab = [&](int c, int k0, float (&v)[8]) {
                 if (h == H) {
+                    const float nb = nb_of(c);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = misc[M_WOUT + k0 + i] * Nb[c];
+                    for (int i = 0; i < 8; ++i) v[i] = misc[M_WOUT + k0 + i] * nb;
                 } else {
                     ld8(row(h + 1, c), k0, v);
                 }

@@ -35,26 +35,61 @@ def capture_graph(device, body, pool=None):
     """ Capture `body()` into a CUDA graph on a side stream.  Unlike the `torch.cuda.graph` context manager this
     does not run the garbage collector and does not empty the allocator cache, which is what makes a capture
     cost ~20 ms there; a fit only pays a millisecond or two here. """
+    import gc
+    _reap()                                          # native objects whose teardown was postponed: now is a safe moment
     graph = torch.cuda.CUDAGraph()
     current = torch.cuda.current_stream(device)
     side = torch.cuda.Stream(device=device)
     side.wait_stream(current)
-    with torch.cuda.stream(side):
-        try:
-            if pool is not None:
-                graph.capture_begin(pool=pool)
-            else:
-                graph.capture_begin()
-            body()
-            graph.capture_end()
-        except Exception:
+    # the collector must not run finalizers while the capture is open: an old engine's __del__ frees device memory
+    # and synchronises streams, which is illegal during a (global-mode) capture and invalidates it
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.stream(side):
             try:
+                if pool is not None:
+                    graph.capture_begin(pool=pool)
+                else:
+                    graph.capture_begin()
+                body()
                 graph.capture_end()
-            except Exception:                       # noqa: BLE001
-                pass
-            raise
+            except Exception:
+                try:
+                    graph.capture_end()
+                except Exception:                       # noqa: BLE001
+                    pass
+                raise
+    finally:
+        if gc_was_enabled:
+            gc.enable()
     current.wait_stream(side)
     return graph
+
+
+_graveyard = []                                      # (destroy function, handle) postponed because a capture was open
+
+
+def _capturing():
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:                                # noqa: BLE001
+        return False
+
+
+def _destroy(fn, handle):
+    """ Tear a native object down now, or — inside a stream capture, where freeing device memory is illegal — later. """
+    if _capturing():
+        _graveyard.append((fn, handle))
+    else:
+        fn(handle)
+
+
+def _reap():
+    if _graveyard and not _capturing():
+        pending, _graveyard[:] = list(_graveyard), []
+        for fn, handle in pending:
+            fn(handle)
 
 
 def shard_batch(batch_size, world, rank):
@@ -165,7 +200,7 @@ class FusedEngine:
         try:
             self._drop_graphs()
             if getattr(self, 'comm', None):
-                self.lib.pinn_comm_destroy(self.comm)
+                _destroy(self.lib.pinn_comm_destroy, self.comm)
                 self.comm = None
             for entry in getattr(self, '_constraint_plans', {}).values():
                 if entry is not None and entry.get('plan'):
@@ -292,7 +327,7 @@ class FusedEngine:
     def _drop_graphs(self):
         self._graphs = {}
         for pipe in getattr(self, '_pipes', {}).values():
-            self.lib.pinn_pipe_destroy(pipe)
+            _destroy(self.lib.pinn_pipe_destroy, pipe)
         self._pipes = {}
 
     def _pinned_losses(self, n):
@@ -515,7 +550,9 @@ class FusedEngine:
                     # be preceded by a dry run: the capture itself is side-effect free
                     graph = capture_graph(self.device, body)
                     self._graphs[key] = graph
-                except Exception:                     # capture unsupported here: plain launches
+                except Exception as exc:              # capture unsupported here: plain launches  # noqa: BLE001
+                    import warnings
+                    warnings.warn('pydens_b200: CUDA-graph capture of the step failed (%s); using plain launches' % exc)
                     graph = None
                     torch.cuda.synchronize(self.device)
             if graph is not None:
@@ -604,7 +641,9 @@ class FusedEngine:
                                                         pool=graphs[0].pool() if graphs else None))
                         self._graphs[key] = graphs
                         exec_ptrs = [g.raw_cuda_graph_exec() for g in graphs]
-                    except Exception:               # capture unsupported here: keep plain launches
+                    except Exception as exc:        # capture unsupported here: keep plain launches  # noqa: BLE001
+                        import warnings
+                        warnings.warn('pydens_b200: CUDA-graph capture of the step failed (%s); using plain launches' % exc)
                         exec_ptrs = None
                         torch.cuda.synchronize(self.device)
             self.steps_done = start + niters

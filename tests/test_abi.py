@@ -78,7 +78,7 @@ def test_variant_tables_point_at_the_right_kernel_instantiations():
 
     class Variant(C.Structure):
         _fields_ = [('nf', C.c_int), ('ns', C.c_int), ('smem_fn', C.c_void_p), ('gmem_fn', C.c_void_p),
-                    ('smem_gen_fn', C.c_void_p), ('gmem_gen_fn', C.c_void_p), ('maxt', C.c_int)]
+                    ('smem_gen_fn', C.c_void_p), ('gmem_gen_fn', C.c_void_p), ('multi_fn', C.c_void_p), ('maxt', C.c_int)]
 
     def stub(nf, ns, gmem, maxt, gen):
         name = '_ZN4pinn11step_kernelILi%dELi%dELb%dELi%dELi16ELb%dEEEvNS_7DevPlanENS_8StepArgsE' % (nf, ns, gmem, maxt, gen)
@@ -97,4 +97,7 @@ def test_variant_tables_point_at_the_right_kernel_instantiations():
                 assert smem == stub(nf, ns, 0, maxt, gen) and gmem == stub(nf, ns, 1, maxt, gen), (nf, ns, gen)
                 other = (v.smem_fn, v.gmem_fn) if gen else (v.smem_gen_fn, v.gmem_gen_fn)
                 assert other == (None, None)           # the sibling unit fills the other half (merged at plan creation)
+                # the persistent multi-step kernel rides in the general half
+                mname = '_ZN4pinn17multi_step_kernelILi%dELi%dELi%dELi16EEEvNS_7DevPlanENS_9MultiArgsE' % (nf, ns, maxt)
+                assert v.multi_fn == (C.cast(getattr(lib, mname), C.c_void_p).value if gen else None)
             assert not fn(nf + 1) and not fn(-1)
