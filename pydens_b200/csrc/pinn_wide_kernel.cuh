@@ -102,20 +102,24 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
 // that issues.  Keeping the election inside the asm keeps the surrounding C++ uniform.
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                        uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-                 "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n"
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "setp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n"
                  :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\t"
-                 "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}\n"
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}\n"
                  :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {      // whole warp; the elected lane commits
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {      // one (elected) lane
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 // Wait for the MMAs committed to `bar`; a tensor-core fault must surface as a launch error, not as a hung GPU.
 // try_wait suspends the warp by itself (the waiting warps must not steal issue slots from the issuing ones).
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     MmaCtx mc;
-    mc.tmem = s_tmem; mc.smem_base = smem_u32(smem);
+    if (s_tmem != 0u) __trap();                              // all 512 columns are ours: the allocation starts at column 0, lane 0
+    mc.tmem = 0u; mc.smem_base = smem_u32(smem);
     const uint32_t tm_lane = mc.tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's TMEM lanes
     uint32_t phase = 0;
     {
@@ -340,10 +345,13 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
         proxy_fence();
         tc_fence_before();
         __syncthreads();
-        if (warp_u < 4) {                                    // warp-uniform: all lanes walk the issue code, one lane issues
+        if (warp_u < 4) {                                    // warp-uniform branch; one elected lane issues the whole share
             tc_fence_after();
-            issue(warp_u);
-            tc_commit(&s_bar);
+            if (elect_one()) {
+                issue(warp_u);
+                tc_commit(&s_bar);
+            }
+            __syncwarp();
         }
         mma_wait(&s_bar, phase);
         phase ^= 1u;

@@ -19,3 +19,15 @@ for per_graph in ('1', '4', '16', '64'):
     torch.cuda.synchronize(); dt = time.perf_counter() - t
     print('steps/graph %3s: 1500 x batch 100 in %.1f ms  (%.1f us/step, %.3g points/s), final loss %.4f'
           % (per_graph, dt * 1e3, dt / 1500 * 1e6, 150000 / dt, float(np.mean(solver.losses[-20:]))))
+
+# persistent multi-step kernel: k whole optimizer steps (Adam included) per launch
+os.environ.pop('PYDENS_B200_GRAPH_STEPS', None)
+for k in (10, 50, 250, 1500):
+    torch.manual_seed(0)
+    solver = Solver(pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh', units=[10, 12, 15, 1])
+    solver.fit(batch_size=100, niters=100, steps_per_launch=k)
+    torch.cuda.synchronize(); t = time.perf_counter()
+    solver.fit(batch_size=100, niters=1500, steps_per_launch=k)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t
+    print('steps_per_launch %4d: 1500 x batch 100 in %.1f ms  (%.1f us/step, %.3g points/s), final loss %.4f'
+          % (k, dt * 1e3, dt / 1500 * 1e6, 150000 / dt, float(np.mean(solver.losses[-20:]))))
