@@ -436,6 +436,10 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
         // level 1: the first linear layer acts on (x, direction vectors, 0) — per thread, no GEMM; only the
         // activations are stored
         float a0h[QN][8];                                    // activations of the current level, this thread's units
+        if (kh == 0) {                                       // the coordinates wait in the exchange area (rows 16..23)
+#pragma unroll
+            for (int k = 0; k < PINN_MAX_DIMS; ++k) Xbuf[(16 + k) * T + p] = x[k];
+        }
         {
             const ActC kc = make_actc(P.layer[0].act);
 #pragma unroll
@@ -515,15 +519,13 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
         // a0h now holds the activations of the top level H
 
         // =========================== ansatz, residual, adjoint seed (one thread per point) ===========================
-        float Nb[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) Nb[c] = 0.0f;
         __syncthreads();                                     // the GA/GB area becomes program scratch
         if (kh == 0) {
+            float Nb[C];
             float* coords = st;
             float* scr = st + (size_t)PINN_MAX_DIMS * RS;
 #pragma unroll
-            for (int k = 0; k < PINN_MAX_DIMS; ++k) coords[(size_t)k * RS] = x[k];
+            for (int k = 0; k < PINN_MAX_DIMS; ++k) coords[(size_t)k * RS] = Xbuf[(16 + k) * T + p];
             float icj[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) icj[c] = 0.0f;
@@ -561,19 +563,12 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
             }
             acc_sbar += ansatz_adjoint<NF, NS>(P, as, ub, Nb);
             acc_bout += Nb[0];
-        }
-        auto nb_of = [&](int c) { return Nb[c]; };
-        // hand Nb to the other threads of the point (the exchange area is free here)
-        __syncthreads();
-        if (kh == 0) {
+            // the adjoint seed of the point goes to the exchange area (rows 0..C-1): every thread of the point reads
+            // it from there when it needs it, instead of carrying C registers through the reverse sweep
 #pragma unroll
             for (int c = 0; c < C; ++c) Xbuf[c * T + p] = Nb[c];
         }
-        __syncthreads();
-        if (kh != 0) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) Nb[c] = Xbuf[c * T + p];
-        }
+        auto nb_of = [&](int c) { return Xbuf[c * T + p]; };
         __syncthreads();
 
         // =========================== reverse ===========================
@@ -586,7 +581,9 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
                 const int k0 = kbeg + q * 8;
                 float t[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = Nb[0] * a0h[q][i];
+                const float nb0 = nb_of(0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = nb0 * a0h[q][i];
                 for (int g = 1; g <= NF; ++g) {
                     float ax[8], ay[8];
                     post_group(H, g, k0, kc, a0h[q], ax, ay);
@@ -609,7 +606,6 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
             tc_fence_before();
         }
         // rounds H..1: adjoint through the activation of level h, then (h >= 2) through the linear layer below it
-        float a0b[QN][8];                                    // activations of level h-1
         for (int h = H; h >= 1; --h) {
             const ActC kc = make_actc(P.layer[h - 1].act);                   // activation of level h
             const ActC kb = make_actc(h >= 2 ? P.layer[h - 2].act : 0);      // activation of level h-1
@@ -618,8 +614,10 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
             if (h >= 2) {
                 __syncthreads();
                 stage_layer(smem, a.params, L, true);
+            }
+            if (h < H) {                                     // (at the top level the forward sweep left them in registers)
 #pragma unroll
-                for (int q = 0; q < QN; ++q) ld8(row(h - 1, 0), kbeg + q * 8, a0b[q]);
+                for (int q = 0; q < QN; ++q) ld8(row(h, 0), kbeg + q * 8, a0h[q]);
             }
             float R[QN][8];                                  // running sum of the value-channel adjoint
 #pragma unroll
@@ -646,7 +644,7 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < PINN_MAX_DIMS; ++i) {
                             if (i < P.total) {
-                                const float xv = (c == 0) ? x[i] : ((c <= NF) ? P.dir_vec[d][i] : 0.0f);
+                                const float xv = (c == 0) ? Xbuf[(16 + i) * T + p] : ((c <= NF) ? P.dir_vec[d][i] : 0.0f);
                                 const float xh = tf32_rn(xv);
                                 *reinterpret_cast<float*>(smem + S_XB_HI + xb_off(1 + i, p)) = xh;
                                 *reinterpret_cast<float*>(smem + S_XB_LO + xb_off(1 + i, p)) = xv - xh;
@@ -700,7 +698,11 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
                     const int k0 = kbeg + q * 8;
                     float dx[8], bx[8], by[8];
                     const float (&a0)[8] = a0h[q];
-                    if (h >= 2) post_group(h - 1, g, k0, kb, a0b[q], bx, by);
+                    if (h >= 2) {
+                        float a0l[8];
+                        ld8(row(h - 1, 0), k0, a0l);
+                        post_group(h - 1, g, k0, kb, a0l, bx, by);
+                    }
                     if (g == 0) {
                         float ab[8];
                         ld_ab(0, k0, ab);
@@ -750,11 +752,6 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
                 }
                 run(group_x(g));
             }
-            // the level below becomes the current level
-#pragma unroll
-            for (int q = 0; q < QN; ++q)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a0h[q][i] = a0b[q][i];
         }
     }
 
