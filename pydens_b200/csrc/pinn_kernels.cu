@@ -21,7 +21,15 @@
 
 #include "pinn_step_kernel.cuh"
 #include "pinn_wide_kernel.cuh"
+#include "pinn_small_kernel.cuh"
 #include "pinn_host_plan.h"
+
+// small_step_kernel instantiations live in pinn_small_nf*.cu
+pinn::MultiKernelFn pinn_small_variant_nf0(int ns);
+pinn::MultiKernelFn pinn_small_variant_nf1(int ns);
+pinn::MultiKernelFn pinn_small_variant_nf2(int ns);
+pinn::MultiKernelFn pinn_small_variant_nf3(int ns);
+pinn::MultiKernelFn pinn_small_variant_nf4(int ns);
 
 // wide_step_kernel instantiations live in pinn_wide_nf*.cu
 pinn::StepKernelFn pinn_wide_variant_nf0(int ns, int threads);
@@ -160,6 +168,8 @@ struct PinnPlan {
     StepKernelFn fn_wide;
     MultiKernelFn fn_multi;                  // persistent multi-step kernel, or nullptr when it does not fit
     int multi_threads, multi_nwacc, multi_smem;
+    MultiKernelFn fn_small;                  // tiny-batch (<= 128 points) variant, or nullptr
+    int small_smem;
     Variant var_store;
     const Variant* var;
     StepKernelFn fn_smem, fn_gmem;           // the pair matching this plan (plain or general)
@@ -299,6 +309,30 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
                     e = allow_max_smem((const void*)p->fn_multi, p->smem_optin);
                     if (e != cudaSuccess) p->fn_multi = nullptr;
                 }
+            }
+            (void)cudaGetLastError();
+        }
+    }
+
+    // ---- tiny batches: the (point, unit)-parallel loop kernel; plain dense chains whose jets fit shared memory ----
+    {
+        p->fn_small = nullptr; p->small_smem = 0;
+        bool plain = s->nf <= 4;
+        for (int l = 0; l < h.n_layers; ++l) if (h.layer[l].skip_src >= 0 || h.layer[l].post_base >= 0) plain = false;
+        if (plain) {
+            MultiKernelFn f = nullptr;
+            switch (s->nf) {
+                case 0: f = pinn_small_variant_nf0(s->ns); break;
+                case 1: f = pinn_small_variant_nf1(s->ns); break;
+                case 2: f = pinn_small_variant_nf2(s->ns); break;
+                case 3: f = pinn_small_variant_nf3(s->ns); break;
+                case 4: f = pinn_small_variant_nf4(s->ns); break;
+            }
+            const int bytes = pinn::small::make_layout(h).total * 4;
+            cudaFuncAttributes fs;
+            if (f && cudaFuncGetAttributes(&fs, (const void*)f) == cudaSuccess && bytes <= p->smem_optin - (int)fs.sharedSizeBytes - 64 &&
+                cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_optin - (int)fs.sharedSizeBytes) == cudaSuccess) {
+                p->fn_small = f; p->small_smem = bytes;
             }
             (void)cudaGetLastError();
         }
@@ -634,7 +668,7 @@ extern "C" int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm, c
 
 extern "C" int pinn_multi_step_max_points(const PinnPlan* p) {
     // one CTA walks the batch tile by tile: any batch works, but the kernel is meant for the launch-bound regime
-    return (p && p->fn_multi) ? 4096 : 0;
+    return (p && p->fn_multi) ? 4096 : ((p && p->fn_small) ? 8 * pinn::small::BP : 0);
 }
 
 extern "C" int pinn_multi_step(const PinnPlan* cp, float* params, float* exp_avg, float* exp_avg_sq, const float* mask,
@@ -645,7 +679,7 @@ extern "C" int pinn_multi_step(const PinnPlan* cp, float* params, float* exp_avg
     PinnPlan* p = const_cast<PinnPlan*>(cp);
     if (!p || !params || !exp_avg || !exp_avg_sq || !mask || !step_counter || !losses_ring)
         return fail(PINN_E_INVALID, "null argument");
-    if (!p->fn_multi) return fail(PINN_E_UNSUPPORTED, "the persistent multi-step kernel does not fit this network in shared memory");
+    if (!p->fn_multi && !p->fn_small) return fail(PINN_E_UNSUPPORTED, "the persistent multi-step kernels do not fit this network in shared memory");
     if (n_points <= 0 || n_points > pinn_multi_step_max_points(p) || k_steps <= 0 || ring_len <= 0 || n_step_tensors < 0)
         return fail(PINN_E_INVALID, "pinn_multi_step: n_points %lld (1..%d), k_steps %d", (long long)n_points, pinn_multi_step_max_points(p), k_steps);
     if (!aligned16(params)) return fail(PINN_E_ALIGN, "params must be 16-byte aligned");
@@ -659,7 +693,29 @@ extern "C" int pinn_multi_step(const PinnPlan* cp, float* params, float* exp_avg
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.opt_step0 = opt_step0;
     a.losses_ring = losses_ring; a.ring_len = ring_len;
     a.n_wacc = p->multi_nwacc; a.rows_total = p->h.rows_total;
-    p->fn_multi<<<1, p->multi_threads, p->multi_smem, (cudaStream_t)stream>>>(plan, a);
+    // batches of at most 128 points: the (point, unit)-parallel kernel (PINN_MULTI_KERNEL=tile forces the other one)
+    const char* mk = getenv("PINN_MULTI_KERNEL");
+    const bool small_ok = p->fn_small && n_points <= 8 * pinn::small::BP && (n_points <= 256 || !p->fn_multi) &&
+                          !(mk && !strcmp(mk, "tile") && p->fn_multi);
+    if (small_ok) {
+        // a cluster of up to 8 CTAs (8 SMs) shares the batch, ~16 points per CTA at least; PINN_SMALL_CLUSTER overrides
+        int nc = (int)((n_points + 15) / 16);
+        if (nc > 8) nc = 8;
+        { const char* e = getenv("PINN_SMALL_CLUSTER"); if (e && atoi(e) >= 1 && atoi(e) <= 8) nc = atoi(e); }
+        while ((n_points + nc - 1) / nc > pinn::small::BP) ++nc;
+        if (nc == 3) nc = 4; else if (nc > 4 && nc < 8) nc = 8;         // cluster sizes 1, 2, 4, 8
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(nc); cfg.blockDim = dim3(pinn::small::NT); cfg.dynamicSmemBytes = p->small_smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, p->fn_small, plan, a));
+    } else {
+        p->fn_multi<<<1, p->multi_threads, p->multi_smem, (cudaStream_t)stream>>>(plan, a);
+    }
     CUDA_TRY(cudaGetLastError());
     return PINN_OK;
 }

@@ -234,10 +234,15 @@ def test_limits_eight_columns_and_deep_network():
 # ---------------------------------------------------------------------------------------------------------------
 # persistent multi-step kernel: k whole optimizer steps (Adam included) per launch — Solver.fit(steps_per_launch=k)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('name,k', [('poisson2d', 8), ('poisson2d', 40), ('ode_param', 5), ('burgers', 7), ('heat1d_icvar', 4)])
-def test_persistent_kernel_follows_the_reference_fit(name, k):
+@pytest.mark.parametrize('kernel', ['small', 'tile'])
+@pytest.mark.parametrize('name,k', [('poisson2d', 8), ('poisson2d', 40), ('ode_param', 5), ('burgers', 7), ('heat1d_icvar', 4),
+                                    ('heat2d', 6), ('wave3d', 4), ('mixed_ic', 5), ('poisson_sin', 10)])
+def test_persistent_kernel_follows_the_reference_fit(name, k, kernel, monkeypatch):
     """ README regime (batch 100): the loss curve of the in-kernel Adam loop against the reference's own Solver.fit
-    on identical points (golden trajectory), same tolerances as the one-launch-per-step path. """
+    on identical points (golden trajectory), same tolerances as the one-launch-per-step path.  Two kernels serve
+    `steps_per_launch`: the (point, unit)-parallel one for batches <= 128 ('small') and the thread-per-point one. """
+    monkeypatch.setenv('PINN_MULTI_KERNEL', kernel)
+    monkeypatch.setenv('PINN_FORCE_KERNEL', 'thread')       # the wide-net problems too (the tile kernel has no multi-step form)
     g = load_golden(name)
     niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
     solver = make_solver(name, g['params'])

@@ -27,14 +27,24 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from pydens_b200 import Solver, D
+    from pydens_b200 import Solver, D, V
 
     def pde(f, x, y):
         return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
     torch.manual_seed(0)
-    solver = Solver(pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh',
-                    units=[10, 12, 15, 1], device=torch.device('cuda', local), backend='fused', seed=7)
-    solver.fit(niters=30, batch_size=100001, lr=0.005)          # odd size: uneven shards
+    problem = sys.argv[2] if len(sys.argv) > 2 else 'readme'
+    if problem == 'readme':
+        solver = Solver(pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh',
+                        units=[10, 12, 15, 1], device=torch.device('cuda', local), backend='fused', seed=7)
+        solver.fit(niters=30, batch_size=100001, lr=0.005)          # odd size: uneven shards
+    else:                                  # a registry problem, e.g. wave3d: the tcgen05 tile kernel under data parallelism
+        import problems as P
+        cfg = P.PROBLEMS[problem]
+        solver = Solver(P.bind(problem, D, lambda n, init: V(n, data=torch.Tensor([init]))), ndims=cfg['ndims'],
+                        nparams=cfg['nparams'], initial_condition=cfg['ic'], boundary_condition=cfg['bc'],
+                        domain=cfg['domain'], layout=cfg['layout'], features=cfg['features'],
+                        activation=cfg['activation'], device=torch.device('cuda', local), backend='fused', seed=7)
+        solver.fit(niters=30, batch_size=40001, lr=0.001)
     losses = [float(v) for v in solver.losses]
     flat = solver.flat_params()
     if world > 1:
@@ -43,7 +53,7 @@ def main():
         assert torch.equal(ref, flat), 'replicas diverged'
     if (not dist.is_initialized()) or dist.get_rank() == 0:
         eng = solver._get_engine()
-        json.dump({'world': world, 'losses': losses, 'params_norm': float(flat.norm()),
+        json.dump({'world': world, 'losses': losses, 'params_norm': float(flat.norm()), 'tensor_core': int(eng.info.tensor_core),
                    'allreduce': 'peer' if eng.comm is not None else ('nccl' if world > 1 else 'none')}, open(out, 'w'))
     if world > 1:
         dist.destroy_process_group()
