@@ -32,7 +32,7 @@ constexpr int SR = BP + 4;              // row stride of every [row][point] arra
 constexpr int NT = 512;
 
 struct Layout {
-    int flat, m1, m2, g, gsum, x, scr, red, lev[PINN_MAX_LAYERS + 2], post_a, post_b, total;   // float offsets
+    int flat, m1, m2, g, gsum, x, scr, red, lev[PINN_MAX_LAYERS + 2], post[PINN_MAX_LAYERS + 2], total;   // float offsets
 };
 __host__ __device__ inline Layout make_layout(const DevPlan& P) {
     const int C = 1 + P.nf + P.ns;
@@ -47,15 +47,13 @@ __host__ __device__ inline Layout make_layout(const DevPlan& P) {
     L.x = o; o += PINN_MAX_DIMS * SR;
     L.scr = o; o += P.n_slots * SR;
     L.red = o; o += (2 + PINN_MAX_VARS) * SR;           // per point: loss, d/dlog_scale, d/dV_i
-    int maxw = 1;
-    L.lev[0] = 0;
+    L.lev[0] = 0; L.post[0] = 0;
     for (int l = 0; l < P.n_layers; ++l) {              // level l+1 = output of layer l, rows (unit, channel)
         L.lev[l + 1] = o; o += P.layer[l].n_out * C * SR;
-        if (P.layer[l].n_out > maxw) maxw = P.layer[l].n_out;
-        if (P.layer[l].n_in > maxw) maxw = P.layer[l].n_in;
+        // post-activation jets of every hidden level stay too: the forward feeds the next layer from them, the
+        // reverse sweep its weight gradients — no recomputation phase, one barrier less per layer
+        L.post[l + 1] = o; if (l + 1 < P.n_layers) o += P.layer[l].n_out * C * SR;
     }
-    L.post_a = o; o += maxw * C * SR;
-    L.post_b = o; o += maxw * C * SR;
     L.total = o;
     return L;
 }
@@ -73,7 +71,6 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
     float* X = smem + Y.x;
     float* scr = smem + Y.scr;
     float* red = smem + Y.red;
-    float* post[2] = {smem + Y.post_a, smem + Y.post_b};
     float* gsum = smem + Y.gsum;
     const int Ln = P.n_layers;
     const int n_out_floats = P.n_params + 4;
@@ -117,8 +114,8 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
         for (int l = 0; l < Ln; ++l) {
             const DevLayer& L = P.layer[l];
             float* out = smem + Y.lev[l + 1];
-            const float* in_post = post[(l + 1) & 1];           // post-activation jets of level l (written in the previous pass)
-            float* out_post = post[l & 1];
+            const float* in_post = smem + Y.post[l];            // post-activation jets of level l (written in the previous pass)
+            float* out_post = smem + Y.post[l + 1];
             const ActC kc = make_actc(L.act);
             const float* W = flat + L.w_off;
             for (int i = tid; i < L.n_out * PS; i += NT) {
@@ -223,21 +220,7 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
             float* dl = smem + Y.lev[l + 1];
             float* cur = smem + Y.lev[l];                        // level l (l >= 1): stored jets, turned into adjoints in place
             const float* W = flat + L.w_off;
-            float* pa = post[0];
-            if (l >= 1) {
-                // (a) post-activation jets of level l, the inputs of this layer
-                const ActC kin = make_actc(P.layer[l - 1].act);
-                for (int i = tid; i < L.n_in * PS; i += NT) {
-                    const int m = i >> ps_log, p = i & (PS - 1);
-                    if (p >= Bp) continue;
-                    float pj[C];
-                    load_post_jet<NF, NS, true>(cur + (size_t)m * C * SR + p, SR, kin, pj);
-                    float* pr = pa + (size_t)m * C * SR + p;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) pr[c * SR] = pj[c];
-                }
-            }
-            __syncthreads();
+            const float* pa = smem + Y.post[l];                  // (a) post-activation jets of level l: kept by the forward sweep
             // (b) weight and bias gradients: entry (j, m), four lanes share the points of an entry
             const int n_e = L.n_out * (L.n_in + 1);
             for (int it = tid; it < ((n_e * 4 + 31) & ~31); it += NT) {
