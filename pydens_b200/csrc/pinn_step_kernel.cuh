@@ -41,8 +41,23 @@ struct StepArgs {
 constexpr int PINN_COMM_FLAGS_OFF = 256;
 constexpr int PINN_COMM_SLOTS_OFF = 1024;
 __host__ __device__ inline size_t comm_slot_floats(int n_out_floats) { return (size_t)((n_out_floats + 31) & ~31); }
+// Small vectors travel in the "LL" form: every float rides in an 8-byte word next to the epoch it belongs to, so a
+// word validates itself — no fence, no separate flag, ONE NVLink traversal between the last fold and the sum.
+constexpr int PINN_COMM_LL_MAX_FLOATS = 4096;
+__host__ __device__ inline bool comm_uses_ll(int n_out_floats) { return n_out_floats <= PINN_COMM_LL_MAX_FLOATS; }
 __host__ __device__ inline size_t comm_bytes(int n_out_floats, int world) {
-    return PINN_COMM_SLOTS_OFF + 2 * (size_t)world * comm_slot_floats(n_out_floats) * sizeof(float);
+    const size_t per_float = comm_uses_ll(n_out_floats) ? 2 * sizeof(float) : sizeof(float);
+    return PINN_COMM_SLOTS_OFF + 2 * (size_t)world * comm_slot_floats(n_out_floats) * per_float;
+}
+// one 8-byte SCALAR access each way: value in the low word, epoch in the high word (single-copy atomic)
+__device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigned int lo, unsigned int hi) {
+    const unsigned long long w = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, unsigned int& lo, unsigned int& hi) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    lo = (unsigned int)w; hi = (unsigned int)(w >> 32);
 }
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -239,6 +254,7 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
             par = (int)(epoch & 1u);
             slot_base = reinterpret_cast<float*>(a.comm_peers[a.comm_rank] + PINN_COMM_SLOTS_OFF);
         }
+        const bool ll = a.comm_world > 1 && comm_uses_ll(n_out_floats);
         for (int i = tid; i < n_out_floats; i += blockDim.x) {
             // partial vectors to fold: the group results (stride FOLD_GROUP slots), or the CTAs of the only group
             float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
@@ -252,7 +268,13 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
             }
             for (; b < n_fold; ++b) s0 += __ldcg(src + (size_t)b * fold_stride);
             const float total = (s0 + s1) + (s2 + s3);
-            if (a.comm_world > 1) {
+            if (ll) {
+                for (int r = 0; r < a.comm_world; ++r) {       // peer stores over NVLink: (value, epoch) in one 8-byte word
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.comm_peers[r] + PINN_COMM_SLOTS_OFF) +
+                                              ((size_t)par * a.comm_world + a.comm_rank) * slot_f;
+                    st_relaxed_sys_v2(dst + i, __float_as_uint(total), epoch);
+                }
+            } else if (a.comm_world > 1) {
                 for (int r = 0; r < a.comm_world; ++r) {       // peer stores over NVLink
                     float* dst = reinterpret_cast<float*>(a.comm_peers[r] + PINN_COMM_SLOTS_OFF) +
                                  ((size_t)par * a.comm_world + a.comm_rank) * slot_f;
@@ -262,7 +284,29 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
                 a.out[i] = total;
             }
         }
-        if (a.comm_world > 1) {
+        if (ll) {
+            // every word carries its epoch: spin on the data itself, sum in rank order (bit-identical on every rank)
+            const unsigned long long* slots = reinterpret_cast<const unsigned long long*>(a.comm_peers[a.comm_rank] + PINN_COMM_SLOTS_OFF) +
+                                              (size_t)par * a.comm_world * slot_f;
+            volatile unsigned int* aborted = reinterpret_cast<volatile unsigned int*>(a.comm_peers[a.comm_rank]) + 1;
+            for (int i = tid; i < n_out_floats; i += blockDim.x) {
+                float sum = 0.0f;
+                bool dead = false;
+                for (int r = 0; r < a.comm_world; ++r) {
+                    unsigned int lo, hi;
+                    ld_relaxed_sys_v2(slots + (size_t)r * slot_f + i, lo, hi);
+                    if (hi != epoch) {
+                        const long long t0 = clock64();
+                        do {
+                            if (*aborted || clock64() - t0 > a.comm_timeout) { *aborted = 1u; dead = true; break; }
+                            ld_relaxed_sys_v2(slots + (size_t)r * slot_f + i, lo, hi);
+                        } while (hi != epoch);
+                    }
+                    sum += __uint_as_float(lo);
+                }
+                a.out[i] = dead ? __int_as_float(0x7fc00000) : sum;
+            }
+        } else if (a.comm_world > 1) {
             __threadfence_system();
             __syncthreads();
             if (tid < a.comm_world) {
