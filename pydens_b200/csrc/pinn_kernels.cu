@@ -170,6 +170,7 @@ struct PinnPlan {
     int multi_threads, multi_nwacc, multi_smem;
     MultiKernelFn fn_small;                  // tiny-batch (<= 128 points) variant, or nullptr
     int small_smem;
+    int wide_ctas;                           // CTAs the tile kernel runs on (<= sm_count)
     Variant var_store;
     const Variant* var;
     StepKernelFn fn_smem, fn_gmem;           // the pair matching this plan (plain or general)
@@ -340,7 +341,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
 
     // ---- wide networks: the tensor-core tile kernel takes the step (PINN_FORCE_KERNEL=thread|wide overrides) ----
     {
-        p->wide = false; p->fn_wide = nullptr;
+        p->wide = false; p->fn_wide = nullptr; p->wide_ctas = p->sm_count;
         int mw = 0;
         const char* fk = getenv("PINN_FORCE_KERNEL");
         const bool eligible = wide_eligible(h, &mw);
@@ -362,6 +363,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
             e = cudaFuncGetAttributes(&fa, (const void*)p->fn_wide);
             if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes(wide): %s", cudaGetErrorString(e)); }
             p->wide = true; p->gmem = true; p->threads = wide_threads; p->n_wacc = 0;
+            p->wide_ctas = p->sm_count;
             p->smem_bytes = pinn::wide::SMEM_BYTES; p->regs = fa.numRegs;
         }
     }
@@ -636,7 +638,9 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
     for (int r = 0; r < PINN_COMM_MAX_RANKS; ++r) a.comm_peers[r] = comm ? comm->peers[r] : nullptr;
     if (p->wide) {
         long long tiles = (n_points + pinn::wide::T - 1) / pinn::wide::T;
-        const int grid = (int)(tiles < p->sm_count ? tiles : p->sm_count);
+        int max_ctas = p->wide_ctas;
+        { const char* e = getenv("PINN_WIDE_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= p->sm_count) max_ctas = atoi(e); }   // experiments
+        const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
         p->fn_wide<<<grid, p->threads, pinn::wide::SMEM_BYTES, st>>>(plan, a);
         CUDA_TRY(cudaGetLastError());
         return PINN_OK;

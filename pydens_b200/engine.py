@@ -48,10 +48,12 @@ def capture_graph(device, body, pool=None):
     try:
         with torch.cuda.stream(side):
             try:
+                # thread-local error mode: other threads (the NCCL watchdog polling its events when the NCCL fallback
+                # all-reduce is part of the step) may keep calling into CUDA while this thread captures
                 if pool is not None:
-                    graph.capture_begin(pool=pool)
+                    graph.capture_begin(pool=pool, capture_error_mode='thread_local')
                 else:
-                    graph.capture_begin()
+                    graph.capture_begin(capture_error_mode='thread_local')
                 body()
                 graph.capture_end()
             except Exception:
@@ -649,6 +651,10 @@ class FusedEngine:
             self.steps_done = start + niters
             torch.cuda.synchronize(self.device)
             vals[:] = loss_host[:niters].numpy()
+        if dist is not None and self.comm is None:
+            # NCCL fallback: the cached graphs hold captured NCCL collectives, and NCCL's communicator teardown
+            # (dist.destroy_process_group) waits for every such graph to be destroyed first — do not keep them
+            self._graphs = {}
         if self.comm is not None:
             aborted = C.c_int(0)
             _native.check(self.lib.pinn_comm_status(self.comm, C.byref(aborted), 1))

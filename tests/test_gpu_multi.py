@@ -21,7 +21,7 @@ def _run(world, out, fused='1', problem='readme'):
     else:
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
                '--master-addr', '127.0.0.1', '--master-port', str(29600 + os.getpid() % 300), script, out, problem]
-    subprocess.check_call(cmd, env=env, timeout=600)
+    subprocess.check_call(cmd, env=env, timeout=240)
     return json.load(open(out))
 
 
