@@ -13,8 +13,8 @@
 // One SM still has to do all of a step's arithmetic, so the batch is further spread over a THREAD-BLOCK CLUSTER of up
 // to 8 CTAs (8 SMs): each CTA keeps a full replica of the parameters and Adam state and takes a contiguous slice of the
 // points; once per step the CTAs exchange their gradient partials through DISTRIBUTED SHARED MEMORY (every CTA sums
-// the 8 partials in rank order, so all replicas apply bit-identical updates) — two cluster barriers per step, nothing
-// leaves the SMs.
+// the 8 partials in rank order, so all replicas apply bit-identical updates) — one cluster barrier per step (the partial
+// buffers alternate), nothing leaves the SMs.
 //
 // Covered: batches of at most 128 points per CTA (1024 per launch), dense chains without residual wiring whose state
 // fits shared memory (everything the README / tutorial problems need).  Selected by pinn_multi_step for such batches.
@@ -42,7 +42,7 @@ __host__ __device__ inline Layout make_layout(const DevPlan& P) {
     L.flat = o; o += np4;
     L.m1 = o; o += np4;
     L.m2 = o; o += np4;
-    L.g = o; o += np4 + 4;
+    L.g = o; o += 2 * (np4 + 4);                        // two partial-gradient buffers, alternating by step parity
     L.gsum = o; o += np4 + 4;
     L.x = o; o += PINN_MAX_DIMS * SR;
     L.scr = o; o += P.n_slots * SR;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
     float* flat = smem + Y.flat;
     float* mom1 = smem + Y.m1;
     float* mom2 = smem + Y.m2;
-    float* g = smem + Y.g;
+    const int g_stride = ((P.n_params + 3) & ~3) + 4;
     float* X = smem + Y.x;
     float* scr = smem + Y.scr;
     float* red = smem + Y.red;
@@ -107,7 +107,15 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
                 for (int k = 0; k < P.total; ++k) X[k * SR + p] = sample_column(P.cols[k], k, gidx, step, a.seed, b0, b1);
             }
         }
+        // the partial gradient alternates between two buffers: a CTA that runs ahead into step s+1 never touches the
+        // buffer its peers may still be reading for step s, so ONE cluster barrier per step is enough
+        float* g = smem + Y.g + (s & 1) * g_stride;
         for (int i = tid; i < n_out_floats; i += NT) g[i] = 0.0f;
+        // Adam's bias corrections do not depend on the gradient: computed here, off the critical path
+        const float t_opt = a.opt_step0 + (float)(s + 1);
+        const float bc1 = 1.0f - powf(a.beta1, t_opt);
+        const float bc2_sqrt = sqrtf(1.0f - powf(a.beta2, t_opt));
+        const float step_size = a.lr / bc1;
         __syncthreads();
 
         // ---- forward: layer l over (output unit j, point p) pairs ------------------------------------------------
@@ -133,6 +141,7 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
                         for (int d = 0; d < NF; ++d) acc[1 + d] = fmaf(w, P.dir_vec[d][k], acc[1 + d]);
                     }
                 } else {
+#pragma unroll 4
                     for (int m = 0; m < L.n_in; ++m) {
                         const float w = W[j * L.n_in + m];
                         const float* r = in_post + (size_t)m * C * SR + p;
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
                         }
                     } else {
                         const float* ar = pa + (size_t)m * C * SR;
+#pragma unroll 4
                         for (int p = sub; p < Bp; p += 4) {
                             float t = 0.0f;
 #pragma unroll
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
                     float ab[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) ab[c] = 0.0f;
+#pragma unroll 4
                     for (int j = 0; j < L.n_out; ++j) {
                         const float w = W[j * L.n_in + m];
                         const float* dr = dl + (size_t)j * C * SR + p;
@@ -285,21 +296,20 @@ __global__ void __launch_bounds__(NT, 1) small_step_kernel(const __grid_constant
         if (csize > 1) {
             cluster.sync();                                      // every CTA's partial [grads | loss] is complete
             for (int i = tid; i < n_out_floats; i += NT) {
+                float v[8];                                      // the remote loads go out together, the sum stays in rank order
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = (r < csize) ? cluster.map_shared_rank(g, r)[i] : 0.0f;
                 float t = 0.0f;
-                for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(g, r)[i];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) t += v[r];
                 gsum[i] = t;
             }
-            cluster.sync();                                      // everybody has read everybody: g may be overwritten
         } else {
             for (int i = tid; i < n_out_floats; i += NT) gsum[i] = g[i];
-            __syncthreads();
         }
+        __syncthreads();
         // ---- Adam (torch.optim.Adam, fused form) on the flat copy ------------------------------------------------------
         {
-            const float t_opt = a.opt_step0 + (float)(s + 1);
-            const float bc1 = 1.0f - powf(a.beta1, t_opt);
-            const float bc2_sqrt = sqrtf(1.0f - powf(a.beta2, t_opt));
-            const float step_size = a.lr / bc1;
             for (int i = tid; i < P.n_params; i += NT) {
                 if (a.mask[i] != 0.0f) {
                     float gi = gsum[i];

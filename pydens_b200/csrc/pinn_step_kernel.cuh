@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
 #pragma unroll
     for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
 
-    for (long long tile = gw; tile < n_tiles; tile += total_warps) {
+    // tiles are dealt warp-slot-major (slot w of every CTA before slot w+1 of any): the last, partial round of tiles
+    // spreads over all SMs instead of filling the first CTAs and leaving the others idle
+    for (long long tile = (long long)warp * gridDim.x + blockIdx.x; tile < n_tiles; tile += total_warps) {
         const long long pl = tile * 32 + lane;
         const bool valid = pl < a.n_points;
         const long long pe = valid ? pl : a.n_points - 1;     // masked lanes replay the last point

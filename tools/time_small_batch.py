@@ -9,7 +9,7 @@ from pydens_b200 import Solver, D
 def pde(f, x, y):
     return D(D(f, x), x) + D(D(f, y), y) - 5 * torch.sin(np.pi * (x + y))
 
-for per_graph in ('1', '4', '16', '64'):
+for per_graph in (() if 'multi' in sys.argv[1:] else ('1', '4', '16', '64')):
     os.environ['PYDENS_B200_GRAPH_STEPS'] = per_graph
     torch.manual_seed(0)
     solver = Solver(pde, ndims=2, boundary_condition=1, layout='fa fa fa f', activation='Tanh', units=[10, 12, 15, 1])
