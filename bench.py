@@ -197,9 +197,22 @@ class Timed:
         self.opt = self.solver.optimizer
         self.ring = torch.zeros(4096, device=dev)
         self._C, self._native = C, _native
+        # the engine's default step: optimizer.step() and the loss log in the tail of the step kernel (pinn_step_adam)
+        self.fused_adam = os.environ.get('PYDENS_B200_FUSED_ADAM', '1') != '0' and (world == 1 or eng.comm is not None)
+        self.adam = None
+        if self.fused_adam:
+            g0 = self.opt.param_groups[0]
+            mask = eng._bind_adam_state(self.opt)
+            m, v, steps, _ = eng._adam_flat
+            self.adam = _native.PinnAdam(m.data_ptr(), v.data_ptr(), mask.data_ptr(), steps.data_ptr(), steps.numel(),
+                                         float(g0['lr']), float(g0['betas'][0]), float(g0['betas'][1]), float(g0['eps']),
+                                         float(g0['weight_decay']), self.ring.data_ptr(), self.ring.numel())
 
     def step(self, pts):
         C, eng = self._C, self.eng
+        if self.fused_adam:
+            eng._step_adam(pts, None, self.local_n, self.inv_n, self.offset, self.adam, allreduce=self.world > 1)
+            return
         eng._step(pts, None, self.local_n, self.inv_n, self.offset, allreduce=self.world > 1)
         if self.world > 1 and eng.comm is None:
             self.dist.all_reduce(eng.out)
@@ -251,15 +264,21 @@ class Timed:
     def kernel_ms(self, reps=5):
         """ the fused kernel alone: CUDA events around K back-to-back launches on the launching stream """
         eng, K = self.eng, self.K
+        if self.fused_adam and self.world == 1:         # the launch of the timed region: Adam + loss log in its tail
+            def launch(pts):
+                eng._step_adam(pts, None, self.local_n, self.inv_n, self.offset, self.adam)
+        else:
+            def launch(pts):
+                eng._step(pts, None, self.local_n, self.inv_n, self.offset)
         for i in range(3):
-            eng._step(self.pool[i % self.pool_n], None, self.local_n, self.inv_n, self.offset)
+            launch(self.pool[i % self.pool_n])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         best = []
         for _ in range(reps):
             e0.record()
             for i in range(K):
-                eng._step(self.pool[i % self.pool_n], None, self.local_n, self.inv_n, self.offset)
+                launch(self.pool[i % self.pool_n])
             e1.record()
             torch.cuda.synchronize()
             best.append(e0.elapsed_time(e1) / K)
@@ -496,6 +515,8 @@ def main():
                               % (t.pool_n, t.pool_n * local_n * total * 4 / 1e6,
                                  ' > L2' if t.pool_n * local_n * total * 4 > 126e6 else ''),
                        cuda_graph=graphed, final_loss=last_loss,
+                       optimizer_step=('torch.optim.Adam update in the tail of the step kernel (pinn_step_adam): one launch '
+                                       'per step' if t.fused_adam else 'torch fused Adam kernels + pinn_record_loss'),
                        allreduce=('in-kernel over NVLink peer memory (pinn_step_allreduce)' if eng.comm is not None
                                   else ('NCCL' if world > 1 else 'none')),
                        kernel='%s<NF=%d,NS=%d> %d threads/CTA x %d CTAs, %d B smem, %d regs, per-point state in %s'
@@ -503,7 +524,7 @@ def main():
                                  info.threads_per_cta, n_ctas, info.smem_bytes, info.regs_per_thread,
                                  'TMEM + L2 slab' if info.tensor_core else ('smem' if info.activations_in_smem else 'gmem'))),
         'value_sampled': sampled_value,
-        'gpu_launches': 2 * K,
+        'gpu_launches': (1 if t.fused_adam else 2) * K,
         'clocks': clk,
         'roofline': roof,
         'hbm': hbm,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   9
+#define PINN_ABI_VERSION   10
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -309,6 +309,32 @@ int pinn_pipe_step(PinnPipe* pipe, int slot, const float* host_points, void* gra
 int pinn_pipe_finish(PinnPipe* pipe, int slot, const float* ring_src, float* loss_dst, void* stream);
 int pinn_pipe_wait(PinnPipe* pipe, int slot);
 int pinn_pipe_sync(PinnPipe* pipe);
+
+/*
+ * ONE fit step INCLUDING optimizer.step() and the loss log: pinn_step / pinn_step_allreduce (model_torch.py:430-460)
+ * with torch.optim.Adam's update (:461) and `losses.append` (:464) executed in the tail of the same kernel by the CTA
+ * that holds the reduced gradient — one launch per step instead of four (step, two fused-Adam kernels, loss record).
+ * `comm` may be NULL (single GPU) or a connected communicator (every rank applies the bit-identical update).
+ * `params` is updated IN PLACE; `grads_and_loss` still receives [grads | loss] of the step.  The Adam state belongs to
+ * the caller (on the Python side: views that torch's optimizer object shares, so `optimizer.step()` and this call are
+ * interchangeable from one step to the next).  t = 1 + max(step_tensors); every step tensor += 1;
+ * losses_ring[*step_counter % ring_len] = loss (skipped when losses_ring is NULL); ++*step_counter.
+ * Capturable in a CUDA graph (the step number and t live on the device).
+ */
+typedef struct PinnAdam {
+    float* exp_avg;            /* device [n_params], in/out */
+    float* exp_avg_sq;         /* device [n_params], in/out */
+    const float* mask;         /* device [n_params]: 1 = trainable, 0 = frozen (left untouched) */
+    float* step_tensors;       /* device [n_step_tensors] fp32 step counters of the optimizer */
+    int32_t n_step_tensors;
+    float lr, beta1, beta2, eps, weight_decay;
+    float* losses_ring;        /* device, or NULL */
+    int64_t ring_len;
+} PinnAdam;
+int pinn_step_adam(const PinnPlan* plan, const PinnComm* comm_or_null, float* params, const float* points,
+                   const PinnColumn* cols, uint64_t seed, uint64_t* step_counter, uint64_t point_offset,
+                   int64_t n_points, float inv_global_n, float* grads_and_loss, float* residual_out,
+                   void* workspace, size_t workspace_bytes, const PinnAdam* adam, void* stream);
 
 /*
  * `k_steps` WHOLE optimizer steps in one launch — the body of the reference loop including optimizer.step()

@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
@@ -70,12 +70,21 @@ class PinnPlanInfo(C.Structure):
     ]
 
 
+class PinnAdam(C.Structure):
+    _fields_ = [
+        ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p), ('mask', C.c_void_p), ('step_tensors', C.c_void_p),
+        ('n_step_tensors', C.c_int32),
+        ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
+        ('losses_ring', C.c_void_p), ('ring_len', C.c_int64),
+    ]
+
+
 EXPORTS = ('pinn_last_error', 'pinn_abi_version', 'pinn_plan_create', 'pinn_plan_destroy',
            'pinn_workspace_bytes', 'pinn_out_floats', 'pinn_step', 'pinn_forward', 'pinn_sample',
            'pinn_record_loss', 'pinn_plan_info', 'pinn_comm_create', 'pinn_comm_connect', 'pinn_comm_destroy',
            'pinn_step_allreduce', 'pinn_comm_status', 'pinn_pipe_create', 'pinn_pipe_destroy', 'pinn_pipe_buffer',
            'pinn_pipe_step', 'pinn_pipe_finish', 'pinn_pipe_wait', 'pinn_pipe_sync', 'pinn_multi_step',
-           'pinn_multi_step_max_points')
+           'pinn_multi_step_max_points', 'pinn_step_adam')
 
 LIB_PATH = os.environ.get('PYDENS_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpinn_b200.so')
 _lib = None
@@ -115,6 +124,9 @@ def load():
                               C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pinn_step_allreduce.argtypes = [C.c_void_p] + lib.pinn_step.argtypes
+    lib.pinn_step_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PinnColumn), C.c_uint64,
+                                   C.c_void_p, C.c_uint64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.POINTER(PinnAdam), C.c_void_p]
     lib.pinn_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     lib.pinn_comm_connect.argtypes = [C.c_void_p, C.c_char_p]
     lib.pinn_comm_destroy.argtypes = [C.c_void_p]

@@ -603,7 +603,8 @@ extern "C" int pinn_pipe_sync(PinnPipe* q) {
 static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* params, const float* points,
                      const PinnColumn* cols, uint64_t seed, const uint64_t* step_counter, uint64_t step_value,
                      uint64_t point_offset, int64_t n_points, float inv_global_n, float* grads_and_loss,
-                     float* residual_out, void* workspace, size_t workspace_bytes, void* stream) {
+                     float* residual_out, void* workspace, size_t workspace_bytes, void* stream,
+                     const PinnAdam* adam = nullptr) {
     PinnPlan* p = const_cast<PinnPlan*>(cp);
     if (!p || !params || !grads_and_loss || !workspace) return fail(PINN_E_INVALID, "null argument");
     if (n_points <= 0) return fail(PINN_E_INVALID, "n_points must be positive");
@@ -625,6 +626,20 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
     a.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_partials_off());
     a.spill = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ws_spill_off(p));
     a.n_wacc = p->n_wacc; a.rows_total = p->h.rows_total;
+    a.adam_m = nullptr; a.adam_v = nullptr; a.adam_mask = nullptr; a.adam_steps = nullptr; a.adam_n_steps = 0;
+    a.adam_lr = a.adam_beta1 = a.adam_beta2 = a.adam_eps = a.adam_wd = 0.0f;
+    a.ring = nullptr; a.ring_len = 1;
+    if (adam) {
+        if (!adam->exp_avg || !adam->exp_avg_sq || !adam->mask || !adam->step_tensors || adam->n_step_tensors < 1)
+            return fail(PINN_E_INVALID, "PinnAdam: null state pointer");
+        if (!step_counter) return fail(PINN_E_INVALID, "pinn_step_adam needs the device step counter");
+        if (adam->losses_ring && adam->ring_len <= 0) return fail(PINN_E_INVALID, "PinnAdam: ring_len must be positive");
+        a.adam_m = adam->exp_avg; a.adam_v = adam->exp_avg_sq; a.adam_mask = adam->mask;
+        a.adam_steps = adam->step_tensors; a.adam_n_steps = adam->n_step_tensors;
+        a.adam_lr = adam->lr; a.adam_beta1 = adam->beta1; a.adam_beta2 = adam->beta2; a.adam_eps = adam->eps;
+        a.adam_wd = adam->weight_decay;
+        a.ring = adam->losses_ring; a.ring_len = adam->losses_ring ? adam->ring_len : 1;
+    }
     static long long comm_timeout = 0;
     if (!comm_timeout) {
         const char* e = getenv("PINN_COMM_TIMEOUT_S");
@@ -668,6 +683,15 @@ extern "C" int pinn_step_allreduce(const PinnPlan* plan, const PinnComm* comm, c
     if (!comm) return fail(PINN_E_INVALID, "null communicator");
     return step_impl(plan, comm, params, points, cols, seed, step_counter, step_value, point_offset, n_points,
                      inv_global_n, grads_and_loss, residual_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pinn_step_adam(const PinnPlan* plan, const PinnComm* comm, float* params, const float* points,
+                              const PinnColumn* cols, uint64_t seed, uint64_t* step_counter, uint64_t point_offset,
+                              int64_t n_points, float inv_global_n, float* grads_and_loss, float* residual_out,
+                              void* workspace, size_t workspace_bytes, const PinnAdam* adam, void* stream) {
+    if (!adam) return fail(PINN_E_INVALID, "null PinnAdam");
+    return step_impl(plan, comm, params, points, cols, seed, step_counter, 0, point_offset, n_points, inv_global_n,
+                     grads_and_loss, residual_out, workspace, workspace_bytes, stream, adam);
 }
 
 extern "C" int pinn_multi_step_max_points(const PinnPlan* p) {

@@ -35,6 +35,16 @@ struct StepArgs {
     char* comm_peers[PINN_COMM_MAX_RANKS]; // exchange buffer of every rank, mapped through CUDA IPC
     int comm_rank, comm_world;
     long long comm_timeout;                // clock64 ticks a rank waits for its peers before poisoning the step
+    // optimizer.step() fused into the tail of the step (pinn_step_adam; adam_m == nullptr: off): torch.optim.Adam on
+    // the flat parameter vector, state shared with the torch optimizer object (its state tensors are views of these)
+    float* adam_m;                         // exp_avg [n_params]
+    float* adam_v;                         // exp_avg_sq [n_params]
+    const float* adam_mask;                // 1 = trainable
+    float* adam_steps;                     // the optimizer's per-parameter step counters (float, device), each += 1
+    int adam_n_steps;
+    float adam_lr, adam_beta1, adam_beta2, adam_eps, adam_wd;
+    float* ring;                           // loss log: ring[step % ring_len] = loss, then the step counter += 1
+    long long ring_len;
 };
 
 // Layout of one rank's exchange buffer (pinn_comm_create): epoch counter, arrival flags, slots.
@@ -190,6 +200,47 @@ __device__ __forceinline__ float fold_column(const float* __restrict__ src, int 
     return (s0 + s1) + (s2 + s3);
 }
 
+// optimizer.step() (reference model_torch.py:461) inside the step kernel: torch.optim.Adam's update, element by element,
+// applied by the thread that has just produced the reduced gradient element.
+struct AdamHyper { float step_size, bc2_sqrt; };
+struct AdamPre { float mk, m0, v0, pv; };
+__device__ __forceinline__ AdamHyper adam_hyper(const StepArgs& a) {
+    AdamHyper h;
+    h.step_size = 0.0f; h.bc2_sqrt = 1.0f;
+    if (a.adam_m) {
+        float t = 0.0f;
+        for (int i = 0; i < a.adam_n_steps; ++i) t = fmaxf(t, a.adam_steps[i]);
+        t += 1.0f;
+        h.step_size = a.adam_lr / (1.0f - powf(a.adam_beta1, t));
+        h.bc2_sqrt = sqrtf(1.0f - powf(a.adam_beta2, t));
+    }
+    return h;
+}
+// the state of element i: loaded BEFORE the gradient element is folded / waited for, so that the latencies overlap
+__device__ __forceinline__ AdamPre adam_load(const StepArgs& a, int i, int n_params) {
+    AdamPre q;
+    q.mk = 0.0f; q.m0 = 0.0f; q.v0 = 0.0f; q.pv = 0.0f;
+    if (a.adam_m && i < n_params) { q.mk = a.adam_mask[i]; q.m0 = a.adam_m[i]; q.v0 = a.adam_v[i]; q.pv = a.params[i]; }
+    return q;
+}
+__device__ __forceinline__ void adam_apply(const StepArgs& a, int i, float g, const AdamPre& q, const AdamHyper& h,
+                                           int n_params) {
+    if (a.adam_m && i == n_params && a.step_ptr) {
+        // element n_params is the loss: `losses.append` (:464) and the step counter, by the thread that produced it
+        // (every CTA read the counter when it started; the next launch is stream-ordered)
+        const unsigned long long s = *a.step_ptr;
+        if (a.ring) a.ring[s % (unsigned long long)a.ring_len] = g;
+        *const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(a.step_ptr)) = s + 1ull;
+    }
+    if (q.mk != 0.0f) {
+        if (a.adam_wd != 0.0f) g = fmaf(a.adam_wd, q.pv, g);
+        const float m1 = fmaf(1.0f - a.adam_beta1, g - q.m0, q.m0);
+        const float m2 = fmaf(a.adam_beta2, q.v0, (1.0f - a.adam_beta2) * g * g);
+        const_cast<float*>(a.params)[i] = q.pv - h.step_size * m1 / (sqrtf(m2) / h.bc2_sqrt + a.adam_eps);
+        a.adam_m[i] = m1; a.adam_v[i] = m2;
+    }
+}
+
 __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_floats) {
     const int tid = threadIdx.x;
     // Two-level fold, fixed order: the last CTA of every group of FOLD_GROUP consecutive CTAs sums its group into
@@ -197,6 +248,8 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
     // was a 7 us serial tail at cfg2 and > 100 us for a 51 KB gradient vector.)
     const int n_groups = ((int)gridDim.x + FOLD_GROUP - 1) / FOLD_GROUP;
     const int group = (int)blockIdx.x / FOLD_GROUP;
+    const int n_params = n_out_floats - 4;
+    const AdamHyper hy = adam_hyper(a);          // bias corrections: every CTA, before it knows whether it is the last
     const int g_first = group * FOLD_GROUP;
     const int g_size = min(FOLD_GROUP, (int)gridDim.x - g_first);
     __threadfence();
@@ -256,6 +309,7 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
         }
         const bool ll = a.comm_world > 1 && comm_uses_ll(n_out_floats);
         for (int i = tid; i < n_out_floats; i += blockDim.x) {
+            const AdamPre pre = (a.comm_world > 1) ? AdamPre{0.0f, 0.0f, 0.0f, 0.0f} : adam_load(a, i, n_params);
             // partial vectors to fold: the group results (stride FOLD_GROUP slots), or the CTAs of the only group
             float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
             int b = 0;
@@ -282,6 +336,7 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
                 }
             } else {
                 a.out[i] = total;
+                adam_apply(a, i, total, pre, hy, n_params);
             }
         }
         if (ll) {
@@ -290,6 +345,7 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
                                               (size_t)par * a.comm_world * slot_f;
             volatile unsigned int* aborted = reinterpret_cast<volatile unsigned int*>(a.comm_peers[a.comm_rank]) + 1;
             for (int i = tid; i < n_out_floats; i += blockDim.x) {
+                const AdamPre pre = adam_load(a, i, n_params);
                 float sum = 0.0f;
                 bool dead = false;
                 for (int r = 0; r < a.comm_world; ++r) {
@@ -304,7 +360,9 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
                     }
                     sum += __uint_as_float(lo);
                 }
-                a.out[i] = dead ? __int_as_float(0x7fc00000) : sum;
+                const float val = dead ? __int_as_float(0x7fc00000) : sum;
+                a.out[i] = val;
+                adam_apply(a, i, val, pre, hy, n_params);
             }
         } else if (a.comm_world > 1) {
             __threadfence_system();
@@ -326,12 +384,20 @@ __device__ __forceinline__ void finish_grid(const StepArgs& a, const int n_out_f
             __syncthreads();
             const float* slots = slot_base + (size_t)par * a.comm_world * slot_f;
             for (int i = tid; i < n_out_floats; i += blockDim.x) {
+                const AdamPre pre = adam_load(a, i, n_params);
                 float s = 0.0f;
                 for (int r = 0; r < a.comm_world; ++r) s += __ldcv(slots + (size_t)r * slot_f + i);
-                a.out[i] = s_timeout ? __int_as_float(0x7fc00000) : s;      // poison instead of hanging
+                const float val = s_timeout ? __int_as_float(0x7fc00000) : s;   // poison instead of hanging
+                a.out[i] = val;
+                adam_apply(a, i, val, pre, hy, n_params);
             }
         }
         if (tid == 0) *a.ticket = 0u;
+        // optimizer.step() (:461) happened element by element above (adam_apply), by the CTA that holds the reduced
+        // gradient: every other CTA of this launch has finished (it took its ticket after its last read of the
+        // parameters), the next launch is stream-ordered.  Left: the optimizer's step counters (every thread of this
+        // CTA read them in adam_hyper, before the barriers above).
+        if (a.adam_m && tid < a.adam_n_steps) a.adam_steps[tid] += 1.0f;
     }
 }
 

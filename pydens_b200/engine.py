@@ -270,6 +270,15 @@ class FusedEngine:
         else:
             _native.check(self.lib.pinn_step(self.plan, *args))
 
+    def _step_adam(self, points, cols, n_points, inv_n, point_offset, adam, allreduce=False):
+        """ The whole step in ONE launch (pinn_step_adam): kernel -> in-kernel all-reduce -> Adam -> loss log. """
+        _native.check(self.lib.pinn_step_adam(
+            self.plan, self.comm if (allreduce and self.comm is not None) else None,
+            C.c_void_p(self.flat.data_ptr()), C.c_void_p(points.data_ptr()) if points is not None else None,
+            cols, C.c_uint64(self.seed), C.c_void_p(self.step_counter.data_ptr()), C.c_uint64(point_offset),
+            C.c_int64(n_points), C.c_float(inv_n), C.c_void_p(self.out.data_ptr()), None,
+            C.c_void_p(self.workspace.data_ptr()), C.c_size_t(self.workspace.numel()), C.byref(adam), self._stream()))
+
     def loss_and_grads(self, points):
         pts = torch.as_tensor(points, dtype=torch.float32).to(self.device).contiguous()
         n = pts.shape[0]
@@ -470,6 +479,24 @@ class FusedEngine:
         entry_ids = {id(p) for p, _ in self.entries}
         stray_params = [p for p in solver.model.parameters() if id(p) not in entry_ids]
 
+        # optimizer.step() inside the step kernel (pinn_step_adam) whenever the optimizer is the plain torch Adam this
+        # engine builds and nothing has to touch the gradient between the kernel and the update
+        g0 = opt.param_groups[0] if opt.param_groups else {}
+        fused_adam = (os.environ.get('PYDENS_B200_FUSED_ADAM', '1') != '0' and type(opt) is torch.optim.Adam
+                      and len(opt.param_groups) == 1 and bool(g0.get('capturable')) and not g0.get('amsgrad')
+                      and not g0.get('maximize') and not torch.is_tensor(g0.get('lr'))
+                      and not fused_constraints and not nums and not stray_params
+                      and (dist is None or self.comm is not None))
+        adam, adam_key = None, None
+        if fused_adam:
+            mask = self._bind_adam_state(opt)          # the optimizer's state tensors become views of flat buffers
+            m_flat, v_flat, steps_flat, _ = self._adam_flat
+            adam = _native.PinnAdam(m_flat.data_ptr(), v_flat.data_ptr(), mask.data_ptr(), steps_flat.data_ptr(),
+                                    steps_flat.numel(), float(g0['lr']), float(g0['betas'][0]), float(g0['betas'][1]),
+                                    float(g0['eps']), float(g0['weight_decay']), self.ring.data_ptr(), self.ring.numel())
+            adam_key = (float(g0['lr']), tuple(float(b) for b in g0['betas']), float(g0['eps']), float(g0['weight_decay']))
+            opt_ready = True                           # the state exists (zeros for a fresh optimizer)
+
         if dist is not None:
             # ranks may reach this fit seconds apart (rank 0 plotting or saving between fits): the in-kernel
             # all-reduce waits only a bounded time for its peers, so line the ranks up first
@@ -504,6 +531,9 @@ class FusedEngine:
                 drained[0] = upto
 
         def one_step(points=None, full_points=None):
+            if fused_adam:
+                self._step_adam(points, cols, local_n, inv_n, point_offset, adam, allreduce=dist is not None)
+                return
             self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
             if dist is not None and self.comm is None:
                 dist.all_reduce(self.out)              # no peer-memory path: NCCL sums [grads | loss]
@@ -529,14 +559,14 @@ class FusedEngine:
                                                     C.c_void_p(self.step_counter.data_ptr()), self._stream()))
 
         capturable = bool(opt.param_groups and opt.param_groups[0].get('capturable', False))
-        graphs_ok = capturable and not nums and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'
+        graphs_ok = (capturable or fused_adam) and not nums and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'
         from .solver import _progress
         done = 0
 
         if host_sampler is None:
             # ---------------- points sampled in the kernel: replay graphs of `per_graph` steps ----------------
             per_graph = int(os.environ.get('PYDENS_B200_GRAPH_STEPS', '0')) or (4 if niters >= 64 else 1)
-            key = ('dev', batch_size, local_n, cols_key, fused_nums, per_graph)
+            key = ('dev', batch_size, local_n, cols_key, fused_nums, per_graph, adam_key)
             graph = self._graphs.get(key) if graphs_ok else None
             if graphs_ok and graph is None and niters >= _GRAPH_MIN_ITERS:
                 if not opt_ready:
@@ -592,7 +622,7 @@ class FusedEngine:
             pinned = self._pinned_batches.get((batch_size, n_stage))
             loss_host = self._pinned_losses(niters)
             loss_ptr = loss_host.data_ptr()
-            key = ('host', batch_size, local_n, n_stage, fused_nums)
+            key = ('host', batch_size, local_n, n_stage, fused_nums, adam_key)
             execs = self._graphs.get(key) if graphs_ok else None
             exec_ptrs = [g.raw_cuda_graph_exec() for g in execs] if execs else None
             keep = [None] * n_stage                    # the tensors whose memory a copy in flight still reads

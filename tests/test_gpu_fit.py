@@ -16,10 +16,13 @@ if torch.cuda.is_available():
     from pydens_b200 import Solver, D, V, NumpySampler
 
 
+@pytest.mark.parametrize('adam', ['kernel', 'torch'])
 @pytest.mark.parametrize('name', list(P.GOLDEN_TRAJ))
-def test_fit_trajectory_matches_reference_fit(name):
+def test_fit_trajectory_matches_reference_fit(name, adam, monkeypatch):
     """ Same init, same point stream, same Adam: the loss curve of the fused fit follows the curve of the
-    reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points). """
+    reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points).  Both forms of
+    optimizer.step(): in the tail of the step kernel (pinn_step_adam, the default) and torch's fused Adam kernels. """
+    monkeypatch.setenv('PYDENS_B200_FUSED_ADAM', '1' if adam == 'kernel' else '0')
     g = load_golden(name)
     niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
     solver = make_solver(name, g['params'])
@@ -273,6 +276,38 @@ def test_persistent_kernel_equals_stepwise_fit_and_keeps_the_optimizer_state():
     c.fit(niters=12, batch_size=100, optimizer=None, steps_per_launch=6)  # and the other way round
     lc = np.asarray(c.losses, dtype=np.float64)
     assert np.max(np.abs(la - lc) / np.maximum(np.abs(la), 1e-6)) <= 1e-3
+
+
+def test_adam_in_the_step_kernel_equals_torch_adam_and_shares_its_state(monkeypatch):
+    """ pinn_step_adam against pinn_step + torch's fused Adam + pinn_record_loss: same loss curve, same parameters, and
+    the torch optimizer object sees the state the kernel wrote (step counters, moments) — a later fit that has to call
+    optimizer.step() itself (an autograd constraint) continues from it. """
+    g = load_golden('poisson2d')
+    runs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('PYDENS_B200_FUSED_ADAM', mode)
+        s = make_solver('poisson2d', g['params'])
+        s.fit(niters=30, batch_size=3000, lr=0.005)                      # in-kernel sampler, graph replay
+        s.fit(niters=13, batch_size=3000, optimizer=None)                # continues on the same optimizer
+        st = [s.optimizer.state[q] for q in s.optimizer.param_groups[0]['params']]     # one fixed order for both modes
+        assert all(abs(float(x['step']) - 43.0) < 0.5 for x in st)
+        runs[mode] = (np.asarray(s.losses, dtype=np.float64), s.flat_params().cpu().numpy(),
+                      torch.cat([x['exp_avg'].reshape(-1) for x in st]).cpu().numpy())
+    la, lb = runs['1'][0], runs['0'][0]
+    assert la.shape == lb.shape == (43,)
+    assert np.max(np.abs(la - lb) / np.maximum(np.abs(lb), 1e-6)) <= 1e-4
+    assert np.linalg.norm(runs['1'][1] - runs['0'][1]) / np.linalg.norm(runs['0'][1]) <= 1e-5
+    assert np.linalg.norm(runs['1'][2] - runs['0'][2]) / np.linalg.norm(runs['0'][2]) <= 1e-3
+    # frozen parameters stay put under the in-kernel update
+    monkeypatch.setenv('PYDENS_B200_FUSED_ADAM', '1')
+    s = make_solver('poisson2d', g['params'])
+    s.model.freeze_trainable(variables=['log_scale'])
+    before = float(s.model.log_scale.detach())
+    w_before = s.flat_params().cpu().numpy().copy()
+    s.fit(niters=10, batch_size=500, lr=0.005)
+    assert float(s.model.log_scale.detach()) == before
+    assert np.abs(s.flat_params().cpu().numpy() - w_before).max() > 0
+    assert len(s.losses) == 10 and np.isfinite(np.asarray(s.losses)).all()
 
 
 def test_persistent_kernel_respects_frozen_parameters():
