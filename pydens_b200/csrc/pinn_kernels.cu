@@ -600,6 +600,25 @@ extern "C" int pinn_pipe_sync(PinnPipe* q) {
     return PINN_OK;
 }
 
+// PINN_PDL=1 launches the step kernels with programmatic stream serialization (the kernel itself waits for its
+// predecessor, griddepcontrol.wait, before it reads anything the predecessor wrote).  Measured on B200 at cfg2: plain
+// back-to-back launches 102.3 -> 100.9 us/step, graph-replayed steps unchanged (100.1 vs 100.7 us) — the graph already
+// has no launch gap to hide — so it stays opt-in.
+static int launch_step(StepKernelFn fn, int grid, int threads, int smem_bytes, cudaStream_t st, const DevPlan& plan,
+                       const StepArgs& a) {
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("PINN_PDL"); pdl = (e && !strcmp(e, "1")) ? 1 : 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, plan, a));
+    return PINN_OK;
+}
+
 static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* params, const float* points,
                      const PinnColumn* cols, uint64_t seed, const uint64_t* step_counter, uint64_t step_value,
                      uint64_t point_offset, int64_t n_points, float inv_global_n, float* grads_and_loss,
@@ -656,15 +675,11 @@ static int step_impl(const PinnPlan* cp, const PinnComm* comm, const float* para
         int max_ctas = p->wide_ctas;
         { const char* e = getenv("PINN_WIDE_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= p->sm_count) max_ctas = atoi(e); }   // experiments
         const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-        p->fn_wide<<<grid, p->threads, pinn::wide::SMEM_BYTES, st>>>(plan, a);
-        CUDA_TRY(cudaGetLastError());
-        return PINN_OK;
+        return launch_step(p->fn_wide, grid, p->threads, pinn::wide::SMEM_BYTES, st, plan, a);
     }
     const int grid = grid_for(p, n_points, p->threads);
     StepKernelFn fn = p->gmem ? p->fn_gmem : p->fn_smem;
-    fn<<<grid, p->threads, p->smem_bytes, st>>>(plan, a);
-    CUDA_TRY(cudaGetLastError());
-    return PINN_OK;
+    return launch_step(fn, grid, p->threads, p->smem_bytes, st, plan, a);
 }
 
 extern "C" int pinn_step(const PinnPlan* plan, const float* params, const float* points, const PinnColumn* cols,

@@ -200,6 +200,13 @@ __device__ __forceinline__ float fold_column(const float* __restrict__ src, int 
     return (s0 + s1) + (s2 + s3);
 }
 
+// Programmatic dependent launch: consecutive steps are launched with programmatic stream serialization, so the CTAs of
+// step s+1 are placed on the SMs as the CTAs of step s drain (fold, all-reduce and Adam run in ONE last CTA) instead
+// of after the whole grid has retired.  pdl_wait() blocks until the previous grid has completed and its writes
+// (parameters, step counter, ticket words) are visible; without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // optimizer.step() (reference model_torch.py:461) inside the step kernel: torch.optim.Adam's update, element by element,
 // applied by the thread that has just produced the reduced gradient element.
 struct AdamHyper { float step_size, bc2_sqrt; };
@@ -412,6 +419,8 @@ __global__ void __launch_bounds__(MAXT, 1) step_kernel(const __grid_constant__ D
     const int n_out_floats = P.n_params + 4;
     const SmemLayout SL = smem_layout(P.weights_floats, n_out_floats, a.n_wacc,
                                       GMEM ? P.n_params : max(P.n_params, a.rows_total * RS * nwarps));
+    pdl_wait();                                    // the previous step (its parameter update) is complete and visible
+    pdl_launch_dependents();                       // the next step's CTAs may take the SMs as ours leave them
     stage_weights(smem, SL, P, a.params);
     const float* sw = smem + SL.weights_f;
     float* wacc_all = smem + SL.wacc_f;

@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(NT, 1) wide_step_kernel(const __grid_constant_
     const int Ln = P.n_layers, H = Ln - 1;
     const int n_out_floats = P.n_params + 4;
 
+    pdl_wait();                                    // the previous step (its parameter update) is complete and visible
+    pdl_launch_dependents();
     // ---- one-time setup: TMEM, barrier, constants --------------------------------------------------------------
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&s_tmem)) : "memory");
