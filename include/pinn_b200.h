@@ -403,6 +403,8 @@ typedef struct PinnPlanInfo {
     int32_t bytes_per_point;          /* algorithmic 4*(ndims+nparams)                   */
     int32_t tensor_core;              /* 1: the tcgen05 / TMEM tile kernel for wide networks runs the step (3xTF32),
                                          0: the thread-per-point FP32 kernel                 */
+    int32_t small_batch_points;       /* largest batch the cluster (point, unit)-parallel loop kernel takes through
+                                         pinn_multi_step (8 CTAs x 128 points), 0: the network does not fit it         */
 } PinnPlanInfo;
 int pinn_plan_info(const PinnPlan* plan, PinnPlanInfo* info);
 

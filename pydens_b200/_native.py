@@ -67,6 +67,7 @@ class PinnPlanInfo(C.Structure):
         ('flops_per_point', C.c_int64),
         ('bytes_per_point', C.c_int32),
         ('tensor_core', C.c_int32),
+        ('small_batch_points', C.c_int32),
     ]
 
 

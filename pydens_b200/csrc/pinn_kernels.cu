@@ -818,6 +818,7 @@ extern "C" int pinn_plan_info(const PinnPlan* p, PinnPlanInfo* info) {
     info->threads_per_cta = p->threads; info->ctas_per_sm = 1;
     info->activations_in_smem = p->gmem ? 0 : 1;
     info->tensor_core = p->wide ? 1 : 0;
+    info->small_batch_points = p->fn_small ? 8 * pinn::small::BP : 0;
     info->smem_bytes = p->smem_bytes; info->regs_per_thread = p->regs; info->sm_count = p->sm_count;
     info->rows_per_point = p->h.rows_total;
     info->flops_per_point = 6ll * C * macs;

@@ -21,6 +21,8 @@ from . import _native
 
 _GRAPH_MIN_ITERS = 8
 _HOST_GRAPH_MIN_ITERS = 8           # host-sampler mode: one capture per staging buffer
+_AUTO_PERSISTENT_STEPS = 50         # optimizer steps per launch when a tiny-batch fit goes to the persistent kernel by itself
+_AUTO_PERSISTENT_MIN_ITERS = 16
 _RING_LEN = 1 << 15                 # device loss ring (steps between two read-backs of a long fit)
 
 
@@ -437,16 +439,28 @@ class FusedEngine:
         solver = self.solver
         steps_per_launch = int(kwargs.pop('steps_per_launch', 0) or 0)
         opt, opt_ready = self._optimizer_for(optimizer, lr, kwargs)
+        # Tiny batches (the README example: batch_size=100, niters=1500) are launch- and latency-bound one step at a
+        # time: when nothing stands in the way, the loop runs in the persistent cluster kernel without being asked to,
+        # _AUTO_PERSISTENT_STEPS optimizer steps per launch (same math, same loss log; PYDENS_B200_AUTO_PERSISTENT=0
+        # keeps one launch per step).  An explicit steps_per_launch takes precedence.
+        requested = steps_per_launch > 0
+        if (not requested and niters >= _AUTO_PERSISTENT_MIN_ITERS and 0 < batch_size <= int(self.info.small_batch_points)
+                and os.environ.get('PYDENS_B200_AUTO_PERSISTENT', '1') != '0' and os.environ.get('PYDENS_B200_NO_GRAPH') != '1'):
+            steps_per_launch = _AUTO_PERSISTENT_STEPS
         if steps_per_launch > 0 and niters > 0:
             g = opt.param_groups[0] if opt.param_groups else {}
             ok = (type(opt) is torch.optim.Adam and len(opt.param_groups) == 1 and not g.get('amsgrad') and not g.get('maximize')
+                  and not torch.is_tensor(g.get('lr'))
                   and _dist() is None and not solver._constraint_numbers(loss_terms)
                   and 0 < batch_size <= self.lib.pinn_multi_step_max_points(self.plan))
-            if ok:
+            if not ok and not requested:
+                steps_per_launch = 0
+            elif ok:
                 if solver.optimizer is not self._opt_obj:
                     self._drop_graphs()
                     self._opt_obj, self._opt_key = solver.optimizer, None
                 return self._fit_persistent(niters, batch_size, sampler, opt, steps_per_launch)
+        if steps_per_launch > 0 and niters > 0:
             import warnings
             warnings.warn('pydens_b200: steps_per_launch ignored (needs Adam, one device, no constraints, a batch of at '
                           'most %d points and a network that fits the persistent kernel)'

@@ -258,8 +258,10 @@ class Solver:
         criterion   default nn.MSELoss(); anything else runs on the autograd path.
         kwargs      forwarded to the optimizer constructor, except
                     steps_per_launch=k  (fused path, small batches): k whole optimizer steps — Adam included — per
-                    launch of a persistent single-CTA kernel; the launch-bound regime of the README example
-                    (batch_size=100, niters=1500) runs several times faster this way.
+                    launch of a persistent kernel.  Batches of at most 1024 points (the launch-bound regime of the
+                    README example, batch_size=100, niters=1500) take this path by themselves, 50 steps per launch,
+                    whenever the optimizer is plain Adam, there is one device and no constraint term
+                    (PYDENS_B200_AUTO_PERSISTENT=0 keeps one launch per step).
         """
         loss_terms = loss_terms if isinstance(loss_terms, (tuple, list)) else (loss_terms,)
         ok, why = self._fused_possible(criterion, loss_terms)

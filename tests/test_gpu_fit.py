@@ -23,6 +23,9 @@ def test_fit_trajectory_matches_reference_fit(name, adam, monkeypatch):
     reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points).  Both forms of
     optimizer.step(): in the tail of the step kernel (pinn_step_adam, the default) and torch's fused Adam kernels. """
     monkeypatch.setenv('PYDENS_B200_FUSED_ADAM', '1' if adam == 'kernel' else '0')
+    # 'torch' also keeps tiny batches on one launch per step; 'kernel' is the default configuration, where they go to the
+    # persistent cluster kernel by themselves
+    monkeypatch.setenv('PYDENS_B200_AUTO_PERSISTENT', '1' if adam == 'kernel' else '0')
     g = load_golden(name)
     niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
     solver = make_solver(name, g['params'])
@@ -260,7 +263,8 @@ def test_persistent_kernel_follows_the_reference_fit(name, k, kernel, monkeypatc
     assert np.linalg.norm(final - g['traj_params']) / np.linalg.norm(g['traj_params']) <= 1e-3
 
 
-def test_persistent_kernel_equals_stepwise_fit_and_keeps_the_optimizer_state():
+def test_persistent_kernel_equals_stepwise_fit_and_keeps_the_optimizer_state(monkeypatch):
+    monkeypatch.setenv('PYDENS_B200_AUTO_PERSISTENT', '0')             # only an explicit steps_per_launch goes persistent here
     g = load_golden('poisson2d')
     a = make_solver('poisson2d', g['params'])
     a.fit(niters=24, batch_size=100, lr=0.005)                           # in-kernel sampler, one launch per step
@@ -308,6 +312,25 @@ def test_adam_in_the_step_kernel_equals_torch_adam_and_shares_its_state(monkeypa
     assert float(s.model.log_scale.detach()) == before
     assert np.abs(s.flat_params().cpu().numpy() - w_before).max() > 0
     assert len(s.losses) == 10 and np.isfinite(np.asarray(s.losses)).all()
+
+
+def test_tiny_batches_go_to_the_persistent_kernel_by_themselves(monkeypatch):
+    """ The README call as written (batch_size=100, no steps_per_launch): same curve as one launch per step, and the
+    engine really took the persistent path (no per-step graphs were captured). """
+    g = load_golden('poisson2d')
+    monkeypatch.setenv('PYDENS_B200_AUTO_PERSISTENT', '0')
+    a = make_solver('poisson2d', g['params'])
+    a.fit(niters=120, batch_size=100, lr=0.005)
+    assert a._engine._graphs
+    monkeypatch.setenv('PYDENS_B200_AUTO_PERSISTENT', '1')
+    b = make_solver('poisson2d', g['params'])
+    b.fit(niters=120, batch_size=100, lr=0.005)
+    assert not b._engine._graphs
+    la, lb = np.asarray(a.losses, dtype=np.float64), np.asarray(b.losses, dtype=np.float64)
+    assert la.shape == lb.shape == (120,)
+    assert np.max(np.abs(la - lb) / np.maximum(np.abs(la), 1e-6)) <= 2e-3
+    b.fit(niters=10, batch_size=100, optimizer=None)                     # too few iterations: stepwise, same optimizer state
+    assert len(b.losses) == 130 and np.isfinite(np.asarray(b.losses)).all()
 
 
 def test_persistent_kernel_respects_frozen_parameters():
