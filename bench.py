@@ -415,6 +415,12 @@ def main():
 
     # ---------------- roofline: the fused kernel alone ----------------
     kern_ms = t.kernel_ms()
+    kern_src = 'CUDA events around K back-to-back plain launches of the step kernel'
+    if t.fused_adam and world == 1 and graphed and ms_total / K < kern_ms:
+        # one launch per step: the timed region IS K launches of this kernel, and the graph replays them with a smaller
+        # inter-launch gap than plain launches leave — the per-launch duration is the step time
+        kern_ms = ms_total / K
+        kern_src = 'the timed region itself: one launch of this kernel per graph-replayed step'
     t_load1 = time.time()
 
     # ---------------- e2e: Solver.fit with host batches (pinned H2D per step, loss D2H per step) --------
@@ -483,7 +489,7 @@ def main():
                     tw = Timed(wl, WORKLOADS[wl][1], dev, rank, world, kk, 3, pool_cap_bytes=1 << 30)
                     tms, _ = tw.run(reps=3)
                     med = sorted(tms)[1] / kk
-                    km = tw.kernel_ms(reps=3)
+                    km = min(tw.kernel_ms(reps=3), med) if tw.fused_adam else tw.kernel_ms(reps=3)
                     roof, _ = roofline_blocks(tw, km, med, clk, _peaks(), wl)
                     other[wl] = {'workload': describe(wl, 1)['workload'], 'ms_per_step': med,
                                  'value': WORKLOADS[wl][1] / (med * 1e-3), 'unit': 'points/s', 'steps': kk,
@@ -500,6 +506,7 @@ def main():
 
     peaks = _peaks()
     roof, hbm = roofline_blocks(t, kern_ms, ms_total / K, clk, peaks, args.workload)
+    roof['kernel_ms_source'] = kern_src
     n_ctas = min(info.sm_count, (local_n + 127) // 128) if info.tensor_core else \
         min(info.sm_count, (local_n + info.threads_per_cta - 1) // info.threads_per_cta)
     line = {
