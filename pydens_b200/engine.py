@@ -165,6 +165,7 @@ class FusedEngine:
         self._graphs, self._pipes, self._pinned_batches = {}, {}, {}
         self._opt_obj, self._opt_key, self._loss_host = None, None, None
         self._adam_flat = None
+        self._adam_bound_to, self._adam_bound_sig = None, None
         self.seed = solver.seed
 
         self.comm = None
@@ -327,10 +328,21 @@ class FusedEngine:
         if (prev is not None and prev is self._opt_obj and key == self._opt_key and optimizer in ('Adam', 'AdamW')
                 and prev.state and not any(kwargs.get(k) for k in ('amsgrad', 'maximize'))):
             with torch.no_grad():
-                for st in prev.state.values():
-                    for v in st.values():
-                        if torch.is_tensor(v):
-                            v.zero_()
+                bound = self._adam_flat is not None and self._adam_bound_to is prev
+                if bound:                                   # the state tensors are views of three flat buffers: three launches
+                    spans = []
+                    for buf in self._adam_flat[:3]:
+                        buf.zero_()
+                        spans.append((buf.data_ptr(), buf.data_ptr() + 4 * buf.numel()))
+                    for st in prev.state.values():          # ... plus whatever state lives elsewhere
+                        for v in st.values():
+                            if torch.is_tensor(v) and not any(a <= v.data_ptr() < e for a, e in spans):
+                                v.zero_()
+                else:
+                    for st in prev.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
             return prev, True
         self._drop_graphs()
         solver._make_optimizer(optimizer, lr, fused_hint=True, **kwargs)
@@ -359,6 +371,11 @@ class FusedEngine:
                                torch.zeros(self.n_params, dtype=torch.float32, device=self.device))
         m, v, steps, mask = self._adam_flat
         in_opt = {id(q) for g in opt.param_groups for q in g['params']}
+        sig = (id(opt), tuple(sorted(in_opt)))
+        if self._adam_bound_to is opt and self._adam_bound_sig == sig and all(
+                (st := opt.state.get(p)) is not None and 'exp_avg' in st and st['exp_avg'].data_ptr() == m.data_ptr() + 4 * o
+                for p, o in self.entries if id(p) in in_opt):
+            return mask                                 # same optimizer, same parameters, still bound: nothing to do
         mask.zero_()
         rebound = False
         with torch.no_grad():
@@ -379,6 +396,7 @@ class FusedEngine:
                 rebound = True
         if rebound:
             self._drop_graphs()                 # captured steps still point at the previous state tensors
+        self._adam_bound_to, self._adam_bound_sig = opt, sig
         return mask
 
     def _fit_persistent(self, niters, batch_size, sampler, opt, k):
