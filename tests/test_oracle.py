@@ -42,3 +42,33 @@ def test_port_trajectory_matches_reference_fit(name):
     ref = g['traj_losses']
     assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 1e-3
     assert abs(losses[-1] - ref[-1]) <= 1e-5 * max(1.0, abs(ref[-1]))
+
+
+@pytest.mark.parametrize('weight_decay', [0.0, 0.01])
+def test_adam_restatement_matches_torch_adam(weight_decay):
+    """ oracle/adam.py (the arithmetic of the step kernel's optimizer tail) against torch.optim.Adam itself — the
+    optimizer the reference constructs (model_torch.py:419-422) and steps (:461) — over 200 steps of random gradients,
+    with a frozen slice. """
+    import torch
+    from oracle import adam as oadam
+    rng = np.random.default_rng(5)
+    n = 373
+    p0 = rng.standard_normal(n).astype(np.float32)
+    w = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    frozen = torch.nn.Parameter(torch.from_numpy(p0[:7].copy()), requires_grad=False)
+    opt = torch.optim.Adam([w], lr=0.005, weight_decay=weight_decay)
+    p, m, v = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    pf, mf, vf = p0[:7].copy(), np.zeros(7, np.float32), np.zeros(7, np.float32)
+    for t in range(1, 201):
+        g = (rng.standard_normal(n) * (10.0 ** rng.uniform(-4, 1))).astype(np.float32)
+        w.grad = torch.from_numpy(g.copy())
+        opt.step()
+        oadam.adam_step(p, g, m, v, t, lr=0.005, weight_decay=weight_decay)
+        oadam.adam_step(pf, g[:7], mf, vf, t, mask=np.zeros(7))
+    ref = w.detach().numpy()
+    assert np.max(np.abs(p - ref)) <= 5e-6                     # parameters are O(1): a few fp32 ulps accumulated over 200 steps
+    st = opt.state[w]
+    rm, rv = st['exp_avg'].numpy(), st['exp_avg_sq'].numpy()
+    assert np.max(np.abs(m - rm)) <= 1e-5 * np.max(np.abs(rm))        # a signed running mean: absolute, not per element
+    assert np.max(np.abs(v - rv)) <= 1e-5 * np.max(np.abs(rv))
+    assert np.array_equal(pf, frozen.detach().numpy()) and not mf.any() and not vf.any()
