@@ -4,17 +4,31 @@
 // with g++ and drives them one point at a time, so the forward jets, ansatz, residual programs and
 // the hand-derived reverse sweep can be checked against the oracle on a machine without a GPU.
 // The warp-level gradient reduction is replaced by direct accumulation (emit_entries' host branch).
+// The per-point storage is laid out as on the device: rows of 32 lanes (row stride RS = 32), the point in one lane,
+// every other lane poisoned with NaN — an access that forgets the row stride or strays into a neighbour's lane shows
+// up as NaN in the result instead of passing by accident.
 // Never loaded by the product (pydens_b200/_native.py loads only libpinn_b200.so).
 #include <vector>
+#include <limits>
 #include <string.h>
 #include "../../pydens_b200/csrc/pinn_host_plan.h"
 
 using namespace pinn;
 
+static const int EMUL_RS = 32;                       // the device's row stride (pinn_step_kernel.cuh: RS)
+// what a lane holds when a point starts: on the device the leftovers of the previous tile (finite, arbitrary) — results must
+// not depend on them
+static const float EMUL_STALE = -7.25e3f;
+
+// storage of `rows` rows x 32 lanes, all NaN; the point of index p lives in lane p % 32
+static std::vector<float> poisoned_rows(int rows) {
+    return std::vector<float>((size_t)rows * EMUL_RS, std::numeric_limits<float>::quiet_NaN());
+}
+
 template <int NF, int NS>
 static void run_step(const DevPlan& P, const float* sw, const float* params, const float* points, long long n,
                      float inv_n, float* out, float* residual) {
-    std::vector<float> st(P.rows_total, 0.0f);
+    std::vector<float> st = poisoned_rows(P.rows_total);
     GradSink sink;
     sink.wacc = out;
     sink.atomic = false;
@@ -23,10 +37,13 @@ static void run_step(const DevPlan& P, const float* sw, const float* params, con
     part.loss = 0.0f; part.sbar = 0.0f;
     for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
     for (long long p = 0; p < n; ++p) {
-        for (int k = 0; k < P.total; ++k) st[k] = points[p * P.total + k];
+        float* lane = st.data() + (p % EMUL_RS);
+        for (int r = 0; r < P.rows_total; ++r) lane[(size_t)r * EMUL_RS] = EMUL_STALE;
+        for (int k = 0; k < P.total; ++k) lane[(size_t)k * EMUL_RS] = points[p * P.total + k];
         // both instantiations the CUDA build uses: the plain one when the plan allows it, else the general one
-        float r = P.general ? point_step<NF, NS, 16, true>(P, sw, params, st.data(), 1, true, inv_n, sink, part)
-                            : point_step<NF, NS, 16, false>(P, sw, params, st.data(), 1, true, inv_n, sink, part);
+        float r = P.general ? point_step<NF, NS, 16, true>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part)
+                            : point_step<NF, NS, 16, false>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part);
+        for (int q = 0; q < P.rows_total; ++q) lane[(size_t)q * EMUL_RS] = std::numeric_limits<float>::quiet_NaN();
         if (residual) residual[p] = r;
     }
     out[P.n_params] += part.loss;
@@ -60,10 +77,13 @@ extern "C" int emul_forward(const PinnSpec* spec, const float* params, const flo
     if (rc) return rc;
     std::vector<float> sw(P.weights_floats + 16);
     host_stage_weights(P, params, sw.data());
-    std::vector<float> st(fwd_rows, 0.0f);
+    std::vector<float> st = poisoned_rows(fwd_rows);
     for (long long p = 0; p < n; ++p) {
-        for (int k = 0; k < P.total; ++k) st[k] = points[p * P.total + k];
-        u_out[p] = point_forward<16>(P, sw.data(), params, st.data(), 1, fwd_row_scr);
+        float* lane = st.data() + (p % EMUL_RS);
+        for (int r = 0; r < fwd_rows; ++r) lane[(size_t)r * EMUL_RS] = EMUL_STALE;
+        for (int k = 0; k < P.total; ++k) lane[(size_t)k * EMUL_RS] = points[p * P.total + k];
+        u_out[p] = point_forward<16>(P, sw.data(), params, lane, EMUL_RS, fwd_row_scr);
+        for (int r = 0; r < fwd_rows; ++r) lane[(size_t)r * EMUL_RS] = std::numeric_limits<float>::quiet_NaN();
     }
     return 0;
 }
