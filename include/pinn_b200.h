@@ -172,7 +172,10 @@ typedef struct PinnSpec {
     float    bc_value;
     float    dom_lo[PINN_MAX_DIMS], dom_hi[PINN_MAX_DIMS];
 
-    int32_t  nf, ns;
+    int32_t  nf, ns;                      /* first-order directions, and how many of them (the first ns) also carry a second
+                                             derivative.  nf <= 4: any ns <= nf.  nf = 5, 6 (full Hessians in 3-D, Laplacians
+                                             in 5 / 6 dimensions): ns = nf only — a direction the equation differentiates once
+                                             still carries its second-order channel, with a zero entry in eq_out's partials */
     int32_t  dir_col[PINN_MAX_DIRS];
     float    dir_vec[PINN_MAX_DIRS][PINN_MAX_DIMS];
 

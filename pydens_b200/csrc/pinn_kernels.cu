@@ -38,6 +38,10 @@ pinn::StepKernelFn pinn_wide_variant_nf2(int ns, int threads);
 pinn::StepKernelFn pinn_wide_variant_nf3(int ns, int threads);
 pinn::StepKernelFn pinn_wide_variant_nf4(int ns, int threads);
 
+// step_kernel instantiations for five / six derivative directions live in pinn_variants_hi_nf*.cu
+const pinn::Variant* pinn_variants_hi_nf5(int ns);
+const pinn::Variant* pinn_variants_hi_nf6(int ns);
+
 namespace pinn {
 
 // ---------------------------------------------------------------------------------------------------
@@ -126,6 +130,9 @@ static bool find_variant(int nf, int ns, Variant& out) {
         case 2: a = pinn_variants_nf2(ns); b = pinn_variants_gen_nf2(ns); break;
         case 3: a = pinn_variants_nf3(ns); b = pinn_variants_gen_nf3(ns); break;
         case 4: a = pinn_variants_nf4(ns); b = pinn_variants_gen_nf4(ns); break;
+        // five / six directions: one kernel each (NS = NF, general form, per-point state in global memory)
+        case 5: a = b = pinn_variants_hi_nf5(ns); break;
+        case 6: a = b = pinn_variants_hi_nf6(ns); break;
         default: return false;
     }
     if (!a || !b) return false;
@@ -208,10 +215,19 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         int rc = build_dev_plan(s, p->h, p->fwd_rows, p->fwd_row_scr, msg, sizeof(msg));
         if (rc) { delete p; return fail(rc, "%s", msg); }
     }
-    if (!find_variant(s->nf, s->ns, p->var_store)) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns); }
+    if (!find_variant(s->nf, s->ns, p->var_store)) {
+        delete p;
+        return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d%s", s->nf, s->ns,
+                    s->nf > 4 ? " (more than 4 derivative directions: every direction must carry its second derivative, ns = nf)" : "");
+    }
     var = &p->var_store;
     p->fn_smem = p->h.general ? var->smem_gen_fn : var->smem_fn;
     p->fn_gmem = p->h.general ? var->gmem_gen_fn : var->gmem_fn;
+    // variants that exist in the general form only (nf > 4) serve plain plans with it; without a shared-memory
+    // resident instantiation the per-point state goes to the global area
+    if (!p->fn_gmem) p->fn_gmem = var->gmem_gen_fn;
+    const bool has_smem_form = p->fn_smem != nullptr;
+    if (!p->fn_gmem) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d", s->nf, s->ns); }
     p->spec = *s;
     p->device = device;
     p->var = var;
@@ -230,7 +246,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
 
     const int n_out_floats = s->n_params + 4;
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void*)p->fn_smem);
+    e = cudaFuncGetAttributes(&fa, (const void*)(has_smem_form ? p->fn_smem : p->fn_gmem));
     if (e != cudaSuccess) { delete p; return fail(PINN_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e)); }
     p->regs = fa.numRegs;
     int max_warps_regs = (65536 / (fa.numRegs * 32));
@@ -253,6 +269,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     bool use_smem = best_nw >= 4 || (best_nw >= 2 && max_warps <= 4);
     if (force && !strcmp(force, "smem") && best_nw >= 1) use_smem = true;
     if (force && !strcmp(force, "gmem")) use_smem = false;
+    if (!has_smem_form) use_smem = false;
     if (use_smem) {
         p->gmem = false; p->threads = best_nw * 32; p->n_wacc = best_nwacc;
         SmemLayout SL = smem_layout(h.weights_floats, n_out_floats, best_nwacc,

@@ -489,6 +489,7 @@ OP = dict(CONST=0, COORD=1, VAR=2, ADD=3, SUB=4, MUL=5, DIV=6, NEG=7, MULI=8, AD
 _UNARY_OP = {'neg': 'NEG', 'sin': 'SIN', 'cos': 'COS', 'tan': 'TAN', 'exp': 'EXP', 'log': 'LOG',
              'sqrt': 'SQRT', 'tanh': 'TANH', 'sigmoid': 'SIGMOID', 'abs': 'ABS', 'sign': 'SIGN'}
 MAX_PROG, MAX_SLOTS = 192, 96
+MAX_DIRS = 6                                # derivative directions the kernels carry (include/pinn_b200.h: PINN_MAX_DIRS)
 
 
 class Program:
@@ -695,8 +696,13 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
     T.dirs = list(axes2) + [-1] * len(mixed) + list(axes1)
     T.ns = len(axes2) + len(mixed)
     nf, ns = len(T.dirs), T.ns
+    if nf > MAX_DIRS:
+        raise NotLowerable('more than %d derivative directions' % MAX_DIRS)
     if nf > 4:
-        raise NotLowerable('more than 4 derivative directions')
+        # five / six directions (full Hessians in 3-D, Laplacians in 5-D / 6-D): the library holds ONE kernel per
+        # direction count there, the one in which every direction carries its second derivative — first-order-only
+        # directions are promoted (their second-order channel is computed and meets a zero adjoint seed)
+        T.ns = ns = nf
     C = 1 + nf + ns
     mapping = {uleaf(): chleaf(0)}
     for d, col in enumerate(T.dirs):

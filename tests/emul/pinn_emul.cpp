@@ -41,8 +41,11 @@ static void run_step(const DevPlan& P, const float* sw, const float* params, con
         for (int r = 0; r < P.rows_total; ++r) lane[(size_t)r * EMUL_RS] = EMUL_STALE;
         for (int k = 0; k < P.total; ++k) lane[(size_t)k * EMUL_RS] = points[p * P.total + k];
         // both instantiations the CUDA build uses: the plain one when the plan allows it, else the general one
-        float r = P.general ? point_step<NF, NS, 16, true>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part)
-                            : point_step<NF, NS, 16, false>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part);
+        // (more than 4 directions: the CUDA build has the general instantiation only, also for plain plans)
+        float r;
+        if constexpr (NF > 4) r = point_step<NF, NS, 16, true>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part);
+        else r = P.general ? point_step<NF, NS, 16, true>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part)
+                           : point_step<NF, NS, 16, false>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part);
         for (int q = 0; q < P.rows_total; ++q) lane[(size_t)q * EMUL_RS] = std::numeric_limits<float>::quiet_NaN();
         if (residual) residual[p] = r;
     }
@@ -64,6 +67,7 @@ extern "C" int emul_step(const PinnSpec* spec, const float* params, const float*
     CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2)
     CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
     CASE(4, 0) CASE(4, 1) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+    CASE(5, 5) CASE(6, 6)
 #undef CASE
     snprintf(msg, msg_len, "no variant nf=%d ns=%d", P.nf, P.ns);
     return PINN_E_UNSUPPORTED;

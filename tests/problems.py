@@ -31,6 +31,30 @@ def _heat2d(f, x, y, t, D, V):                       # tutorial heat eq. without
     return D(D(f, x), x) + D(D(f, y), y) - D(f, t)
 
 
+# --- more than four derivative directions (kernels with NF = NS = 5 / 6; the tracer promotes every direction) ---
+def _hess3d(f, x, y, z, D, V):                       # anisotropic diffusion with cross terms: 3 axes + 3 diagonals
+    return (D(D(f, x), x) + 2.0 * D(D(f, y), y) + 3.0 * D(D(f, z), z) + 0.5 * D(D(f, x), y) - 0.3 * D(D(f, y), z)
+            + 0.7 * D(D(f, x), z) - torch.sin(x + y + z) * f)
+
+
+def _heat4d(f, x, y, z, w, t, D, V):                 # heat equation in four space dimensions: 4 second-order + t
+    return D(f, t) - 0.1 * (D(D(f, x), x) + D(D(f, y), y) + D(D(f, z), z) + D(D(f, w), w)) + 0.2 * f
+
+
+def _lap6d(f, a, b, c, d, e, g, D, V):               # Poisson in six dimensions (the DGM paper's regime)
+    return (D(D(f, a), a) + D(D(f, b), b) + D(D(f, c), c) + D(D(f, d), d) + D(D(f, e), e) + D(D(f, g), g)
+            - torch.cos(a + b - c) * (d + e * g))
+
+
+def _hess3d_var(f, x, y, z, D, V):                   # 3 axes + 2 diagonals, a first-order term and a variable
+    return (D(D(f, x), x) + D(D(f, y), y) * V('kappa', 0.6) + D(D(f, z), z) + D(D(f, x), y) - 0.4 * D(D(f, y), z)
+            + f * D(f, z) - V('kappa', 0.6) ** 2)
+
+
+def _ic_heat4d(x, y, z, w):
+    return torch.sin(PI * x) * y * (1.0 - y) + 0.5 * z * w
+
+
 def _heat_param(f, x, y, t, a, D, V):                # tutorial: `- a * D(f, t)`
     return D(D(f, x), x) + D(D(f, y), y) - a * D(f, t)
 
@@ -158,17 +182,32 @@ PROBLEMS = {
     'mixed_acts_skip': dict(equation=_mixed2d, ndims=2, nparams=0, ic=None, bc=0.3, domain=[(0, 2), (-1, 1)],
                             features=[8, 8, 8, 1], activation=[Sin, 'GELU', 'Tanh'], layout='fa R fa fa+ f',
                             ranges=[(0, 2), (-1, 1)]),
+    # five / six derivative directions (HI_DIRECTION below)
+    'hess3d': dict(equation=_hess3d, ndims=3, nparams=0, ic=None, bc=0.2, domain=[(0, 1), (-1, 1), (0, 2)],
+                   features=[12, 10, 1], activation='Tanh', layout='fafaf', ranges=[(0, 1), (-1, 1), (0, 2)]),
+    'heat4d': dict(equation=_heat4d, ndims=5, nparams=0, ic=_ic_heat4d, bc=0, domain=(0, 1),
+                   features=[11, 9, 1], activation='Sigmoid', layout='fafaf', ranges=[(0, 1)] * 4 + [(0, .5)],
+                   log_scale=0.15),
+    'lap6d': dict(equation=_lap6d, ndims=6, nparams=0, ic=None, bc=1, domain=(0, 1),
+                  features=[10, 8, 1], activation='Tanh', layout='fafaf', ranges=[(0, 1)] * 6),
+    'hess3d_var': dict(equation=_hess3d_var, ndims=3, nparams=0, ic=None, bc=-0.1, domain=(0, 1),
+                       features=[8, 8, 8, 1], activation=['GELU', 'Tanh', 'Sigmoid'], layout='fa R fa fa+ f',
+                       variables={'kappa': 0.6}, ranges=[(0, 1)] * 3),
 }
+
+# problems that need the five- / six-direction kernels; the GPU tests of those kernels live in their own file
+HI_DIRECTION = ('hess3d', 'heat4d', 'lap6d', 'hess3d_var')
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
                 'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75,
-                'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60}
+                'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60,
+                'hess3d': 70, 'heat4d': 66, 'lap6d': 75, 'hess3d_var': 68}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
                'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01),
                'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01),
-               'wave3d': (12, 96, 0.001)}
+               'wave3d': (12, 96, 0.001), 'heat4d': (12, 48, 0.01), 'hess3d_var': (12, 40, 0.01)}
 
 
 def make_points(name, batch, seed):

@@ -80,7 +80,12 @@ def test_lowering_decisions():
     s = Solver(lambda f, x, y: D(D(f, x), y), ndims=2, device='cpu')
     assert s._traced is not None and s._traced.dirs == [0, 1, -1]                 # mixed derivative: polarised
     s = Solver(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z), ndims=3, device='cpu')
-    assert s._traced is None and 'directions' in s._lower_error
+    assert s._traced is not None and s._traced.nf == 6 and s._traced.ns == 6      # x, y, z and the three diagonals
+    s = Solver(lambda f, x, y, z, t: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z) - D(f, t), ndims=4, device='cpu')
+    assert s._traced is None and 'directions' in s._lower_error                   # seven: more than the kernels carry
+    s = Solver(lambda f, x, y, z, w, t: D(D(f, x), x) + D(D(f, y), y) + D(D(f, z), z) + D(D(f, w), w) - D(f, t), ndims=5,
+               device='cpu')
+    assert s._traced.nf == 5 and s._traced.ns == 5                                # t promoted to second order
     s = Solver(lambda f, t: D(f, t), ndims=1, initial_condition=lambda: V('init', data=torch.Tensor([3.0])),
                device='cpu')
     assert s._traced is not None and s._traced.var_names == ['init'] and s._traced.ic_has_vars

@@ -126,3 +126,96 @@ def test_random_problem_matches_fp64_oracle(seed):
     ref_u = prob.predict(pts.astype(np.float64))
     # u is a sum of O(1) terms that may cancel: the error is measured against that scale, not against |u|
     assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# five / six derivative directions (kernels step_kernel<5,5> / <6,6>: every direction carries its second derivative)
+# ---------------------------------------------------------------------------------------------------------------
+def _many_direction_equations(ndims):
+    """ (name, callable) candidates whose jet needs 5 or 6 directions in a problem with `ndims` variables. """
+    eqs = []
+    if ndims == 3:
+        eqs += [('hessian3', lambda u, x, y, z, D, V: D(D(u, x), x) + D(D(u, y), y) * 0.5 + D(D(u, z), z) + D(D(u, x), y)
+                 - 0.7 * D(D(u, y), z) + 0.2 * D(D(u, x), z) * u - torch.cos(x * z)),
+                ('two_diagonals', lambda u, x, y, z, D, V: D(D(u, x), y) + D(D(u, y), z) * V('k', 0.7) + D(u, x) * u - y)]
+    if ndims == 4:
+        eqs += [('diag_plus_time', lambda u, x, y, z, t, D, V: D(u, t) - D(D(u, x), x) - D(D(u, y), y) - D(D(u, z), z)
+                 - 0.4 * D(D(u, x), z) + u ** 2),
+                ('wave_cross', lambda u, x, y, z, t, D, V: D(D(u, t), t) - D(D(u, x), x) - D(D(u, y), y) - D(D(u, z), z)
+                 + 0.3 * D(D(u, x), y) - torch.sin(t))]
+    if ndims == 5:
+        eqs += [('heat4', lambda u, a, b, c, d, t, D, V: D(u, t) - 0.2 * (D(D(u, a), a) + D(D(u, b), b) + D(D(u, c), c) + D(D(u, d), d)) + a * u),
+                ('lap5', lambda u, a, b, c, d, e, D, V: D(D(u, a), a) + D(D(u, b), b) + D(D(u, c), c) + D(D(u, d), d) + D(D(u, e), e)
+                 - torch.exp(-u) * V('k', 0.7)),
+                ('first5', lambda u, a, b, c, d, e, D, V: D(u, a) + b * D(u, b) - D(u, c) * D(u, d) + D(u, e) * u - 0.1)]
+    if ndims == 6:
+        eqs += [('lap6', lambda u, a, b, c, d, e, g, D, V: D(D(u, a), a) + D(D(u, b), b) + D(D(u, c), c) + D(D(u, d), d)
+                 + D(D(u, e), e) + D(D(u, g), g) - u * torch.cos(a + g)),
+                ('heat5', lambda u, a, b, c, d, e, t, D, V: D(u, t) * (1.0 + a) - D(D(u, a), a) - D(D(u, b), b) - D(D(u, c), c)
+                 - D(D(u, d), d) - D(D(u, e), e))]
+    return eqs
+
+
+def _random_many_direction_problem(seed):
+    rng = np.random.RandomState(50000 + seed)
+    ndims = int(rng.randint(3, 7))
+    depth = int(rng.randint(1, 4))
+    widths = [int(rng.choice([1, 3, 4, 7, 8, 9, 13, 16, 17, 24])) for _ in range(depth)]
+    acts = [ACTS[int(rng.randint(len(ACTS)))] for _ in range(depth)]
+    layout = ''
+    for l in range(depth):
+        if l >= 1 and 'R' not in layout and rng.rand() < 0.4:
+            widths[l] = widths[l - 1]
+            layout += 'R fa+ '
+        else:
+            layout += 'fa '
+    layout += 'f'
+    eqs = _many_direction_equations(ndims)
+    name, eq = eqs[int(rng.randint(len(eqs)))]
+    has_time = name in ('diag_plus_time', 'wave_cross', 'heat4', 'heat5')
+    has_ic = has_time and bool(rng.rand() < 0.7)
+    nsp = ndims - 1 if has_ic else ndims
+    ic = None
+    if has_ic:
+        ic = (lambda *x: torch.sin(2.0 * x[0]) * x[1] + 0.5 * x[-1]) if rng.rand() < 0.6 else float(np.round(rng.uniform(-1, 2), 2))
+    bc = float(np.round(rng.uniform(-1, 1), 2)) if rng.rand() < 0.6 else None
+    domain = [(float(np.round(rng.uniform(-1, 0.2), 2)), float(np.round(rng.uniform(0.8, 2.5), 2))) for _ in range(ndims)]
+    return dict(ndims=ndims, nparams=0, total=ndims, features=widths + [1], acts=acts, layout=layout, ic=ic, bc=bc,
+                domain=domain, eq=eq, eq_name=name, ranges=domain, variables={'k': 0.7} if name in ('two_diagonals', 'lap5') else None,
+                log_scale=float(np.round(rng.uniform(-0.5, 0.5), 2)))
+
+
+@pytest.mark.parametrize('seed', list(range(40)))
+def test_random_many_direction_problem_matches_fp64_oracle(seed):
+    cfg = _random_many_direction_problem(seed)
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    nsp = cfg['ndims'] - 1 if cfg['ic'] is not None else cfg['ndims']
+    traced = T.trace(lambda u, *xs: cfg['eq'](u, *xs, D=T.sym_D, V=sym_V), cfg['total'], None,
+                     initial_condition=cfg['ic'], ndims_spatial=nsp)
+    assert traced.nf in (5, 6) and traced.ns == traced.nf, cfg['eq_name']
+    acts, skips = _layer_plan(cfg)
+    spec = N.build_spec([cfg['total']] + cfg['features'], acts, cfg['ndims'], 0, cfg['bc'] is not None,
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, cfg['ic'] is not None, cfg['domain'], traced,
+                        skips=skips)
+    prob = ap.Problem(cfg['eq'], ndims=cfg['ndims'], nparams=0, initial_condition=cfg['ic'],
+                      boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
+                      activation=cfg['acts'], dtype=torch.float64, variables=cfg['variables'], seed=seed,
+                      layout=cfg['layout'])
+    with torch.no_grad():
+        prob.log_scale.fill_(cfg['log_scale'])
+    params = prob.flat_params().numpy()
+    assert spec.n_params == params.size
+    rng = np.random.RandomState(2000 + seed)
+    n = int(rng.choice([1, 7, 33, 64]))
+    pts = np.concatenate([rng.uniform(lo, hi, size=(n, 1)) for lo, hi in cfg['ranges']], axis=1).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params.astype(np.float32), pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float32).astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    tag = '%s %s %s acts=%s' % (cfg['eq_name'], cfg['layout'], cfg['features'], acts)
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 2e-5 * cond * max(abs(ref_loss), 1e-6), tag
+    assert rel_l2(residual, ref_res) <= 2e-5 * cond, tag
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, tag
+    u = E.emul_forward(spec, params.astype(np.float32), pts)
+    ref_u = prob.predict(pts.astype(np.float64))
+    assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag

@@ -17,7 +17,7 @@ if torch.cuda.is_available():
 
 
 @pytest.mark.parametrize('adam', ['kernel', 'torch'])
-@pytest.mark.parametrize('name', list(P.GOLDEN_TRAJ))
+@pytest.mark.parametrize('name', [n for n in P.GOLDEN_TRAJ if n not in P.HI_DIRECTION])
 def test_fit_trajectory_matches_reference_fit(name, adam, monkeypatch):
     """ Same init, same point stream, same Adam: the loss curve of the fused fit follows the curve of the
     reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points).  Both forms of

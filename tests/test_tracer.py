@@ -87,14 +87,32 @@ def test_not_lowerable_cases():
     D = T.sym_D
     with pytest.raises(T.NotLowerable):            # third order
         T.trace(lambda f, x: D(D(D(f, x), x), x), 1, None)
-    with pytest.raises(T.NotLowerable):            # more than 4 directions (3 axes + 2 diagonals)
-        T.trace(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z), 3, None)
+    with pytest.raises(T.NotLowerable):            # more than 6 directions (3 axes + 3 diagonals + t)
+        T.trace(lambda f, x, y, z, t: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z) + D(f, t), 4, None)
     with pytest.raises(T.NotLowerable):            # data-dependent branch
         T.trace(lambda f, x: f if x > 0 else -f, 1, None)
     with pytest.raises(T.NotLowerable):            # unsupported torch function
         T.trace(lambda f, x: torch.cumsum(f, 0), 1, None)
     with pytest.raises(T.NotLowerable):            # initial condition depending on the solution
         T.trace(lambda f, x: D(f, x), 1, None, initial_condition=lambda: T.Sym(T.uleaf()), ndims_spatial=0)
+
+
+def test_five_and_six_directions_are_promoted_to_second_order():
+    """ More than 4 directions: the library holds one kernel per direction count (NS = NF), so every direction
+    carries its second-order channel; the residual's partials with respect to the promoted channels are zero. """
+    D = T.sym_D
+    tr = T.trace(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z), 3, None)          # 3 axes + 2 diagonals
+    assert (tr.nf, tr.ns) == (5, 5) and tr.dirs == [0, 1, 2, -1, -1]
+    tr = T.trace(lambda f, x, y, z, w, t: D(D(f, x), x) + D(D(f, y), y) + D(D(f, z), z) + D(D(f, w), w) - D(f, t) * t, 5, None,
+                 initial_condition=lambda x, y, z, w: x * y + z * w, ndims_spatial=4)
+    assert (tr.nf, tr.ns) == (5, 5) and tr.dirs == [0, 1, 2, 3, 4] and tr.channels == 11
+    # channel layout: 0 value, 1..5 first order, 6..10 second order; t (direction 4) has no second derivative in the
+    # equation: d residual / d channel 10 is the constant 0
+    rng = np.random.RandomState(0)
+    coords, jet = rng.uniform(0.2, 0.9, size=(5, 7)), rng.normal(size=(11, 7))
+    outs = T.run_program(tr.eq_prog, jet, coords, [])
+    assert np.all(outs[1 + 10] == 0.0) and np.allclose(outs[1 + 5], -coords[4])
+    np.testing.assert_allclose(outs[0], jet[6] + jet[7] + jet[8] + jet[9] - jet[5] * coords[4], rtol=1e-12)
 
 
 def test_variables_inside_initial_condition():
