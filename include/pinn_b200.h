@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION   10
+#define PINN_ABI_VERSION   11
 
 #define PINN_MAX_LAYERS    16   /* linear layers                                   */
 #define PINN_MAX_DIMS       8   /* ndims + nparams (columns of the point matrix)   */
@@ -187,6 +187,12 @@ typedef struct PinnSpec {
     int32_t   ic_out[(1 + 2 * PINN_MAX_DIRS) * (1 + PINN_MAX_VARS)];
     int32_t   ic_has_vars;
     int32_t   n_slots;          /* scratch slots either program may touch */
+    int32_t   order;            /* 0 (or 2): derivatives up to order 2, channels = value, nf firsts, ns seconds (above).
+                                   3 or 4 (D nested three / four times, model_torch.py:174-178: u_xxx of KdV, u_xxxx of beam
+                                   equations): EVERY direction carries its Taylor jet up to this order — channel
+                                   1 + d*order + (k-1) holds the k-th derivative along direction d, channels = 1 + nf*order;
+                                   ns is ignored (0); nf <= 3, axis-aligned directions (dir_col[d] >= 0), plain dense chains
+                                   with tanh / sigmoid, no variables inside the initial condition */
 } PinnSpec;
 
 typedef struct PinnPlan PinnPlan;

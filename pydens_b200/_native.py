@@ -6,7 +6,7 @@ module raises — there is no CPU or eager fallback behind it.
 import ctypes as C
 import os
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_LAYERS, MAX_DIMS, MAX_DIRS, MAX_VARS, MAX_PROG, MAX_SLOTS = 16, 8, 6, 4, 192, 96
 
 ACT = {'none': 0, 'tanh': 1, 'sigmoid': 2, 'sin': 3, 'softplus': 4, 'silu': 5, 'gelu': 6}
@@ -54,6 +54,7 @@ class PinnSpec(C.Structure):
         ('ic_out', C.c_int32 * ((1 + 2 * MAX_DIRS) * (1 + MAX_VARS))),
         ('ic_has_vars', C.c_int32),
         ('n_slots', C.c_int32),
+        ('order', C.c_int32),
     ]
 
 
@@ -239,6 +240,7 @@ def build_spec(widths, acts, ndims, nparams, has_bc, bc_value, has_ic, domain, t
     for i in range(ndims):
         s.dom_lo[i], s.dom_hi[i] = float(domain[i][0]), float(domain[i][1])
     s.nf, s.ns = traced.nf, traced.ns
+    s.order = int(getattr(traced, 'order', 2)) if getattr(traced, 'order', 2) > 2 else 0
     for d, vec in enumerate(traced.dir_vecs):
         s.dir_col[d] = traced.dirs[d]
         for k, v in enumerate(vec):

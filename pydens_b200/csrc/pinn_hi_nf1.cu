@@ -1,0 +1,8 @@
+// hi_step_kernel instantiations for 1 derivative direction(s), orders 3 and 4 (see pinn_hi_kernel.cuh)
+#include "pinn_hi_kernel.cuh"
+
+pinn::StepKernelFn pinn_hi_variant_nf1(int order) {
+    if (order == 3) return pinn::hi::hi_step_kernel<1, 3>;
+    if (order == 4) return pinn::hi::hi_step_kernel<1, 4>;
+    return nullptr;
+}

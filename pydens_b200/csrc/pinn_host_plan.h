@@ -36,6 +36,10 @@ inline int validate_prog(const PinnInstr* prog, int n, int n_slots, int total, i
     return PINN_OK;
 }
 
+// Derivative order of a spec: 2 (value / first / second channels), or 3 / 4 (whole jets per direction, pinn_device_hi.cuh).
+inline int spec_order(const PinnSpec* s) { return s->order >= 3 ? s->order : 2; }
+inline int spec_channels(const PinnSpec* s) { return s->order >= 3 ? 1 + s->nf * s->order : 1 + s->nf + s->ns; }
+
 // Fills `h` (device plan, minus anything that needs a device) and the forward-only row layout.
 inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd_row_scr, char* msg, size_t msg_len) {
     if (s->abi_version != PINN_ABI_VERSION)
@@ -50,7 +54,27 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     if (s->n_params <= 0 || (s->n_params & 3)) PINN_PLAN_FAIL(PINN_E_INVALID, "n_params must be a positive multiple of 4");
     if (s->nf < 0 || s->nf > PINN_MAX_DIRS || s->ns < 0 || s->ns > s->nf) PINN_PLAN_FAIL(PINN_E_INVALID, "jet set nf=%d ns=%d", s->nf, s->ns);
     if (s->n_vars < 0 || s->n_vars > PINN_MAX_VARS) PINN_PLAN_FAIL(PINN_E_INVALID, "n_vars");
-    const int C = 1 + s->nf + s->ns;
+    if (s->order != 0 && (s->order < 2 || s->order > 4)) PINN_PLAN_FAIL(PINN_E_INVALID, "derivative order %d (2..4)", s->order);
+    const bool hi = s->order >= 3;
+    if (hi) {
+        // whole-jet plans (pinn_device_hi.cuh): what that code covers
+        if (s->nf < 1 || s->nf > 3) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d with %d derivative directions (1..3)", s->order, s->nf);
+        if (s->ns != 0) PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: ns must be 0 (every direction carries its whole jet)", s->order);
+        for (int d = 0; d < s->nf; ++d) {
+            if (s->dir_col[d] < 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: direction %d is not an axis", s->order, d);
+            for (int e = 0; e < d; ++e)
+                if (s->dir_col[e] == s->dir_col[d]) PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
+        }
+        if (s->has_ic && s->ic_has_vars) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: variables inside the initial condition", s->order);
+        for (int l = 0; l < Ln; ++l) {
+            if (s->skip_src[l] >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: residual layouts", s->order);
+            if (s->act[l] != PINN_ACT_NONE && s->act[l] != PINN_ACT_TANH && s->act[l] != PINN_ACT_SIGMOID)
+                PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: activation %d (tanh / sigmoid only)", s->order, s->act[l]);
+        }
+    }
+    const int C = spec_channels(s);
+    if (1 + C + s->n_vars > (int)(sizeof(s->eq_out) / sizeof(s->eq_out[0])))
+        PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "%d jet channels + %d variables exceed the program's outputs", C, s->n_vars);
     for (int d = 0; d < s->nf; ++d) {
         if (s->dir_col[d] >= total) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_col[%d]", d);
         bool any = false;
@@ -80,7 +104,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     h.n_layers = Ln; h.total = total; h.ndims = s->ndims; h.nparams = s->nparams;
     h.has_bc = s->has_bc ? 1 : 0; h.has_ic = s->has_ic ? 1 : 0;
     h.nsp = s->has_ic ? s->ndims - 1 : s->ndims;
-    h.nf = s->nf; h.ns = s->ns; h.n_params = s->n_params; h.log_scale_off = s->log_scale_off;
+    h.nf = s->nf; h.ns = hi ? 0 : s->ns; h.n_params = s->n_params; h.log_scale_off = s->log_scale_off;
     h.n_vars = s->n_vars; h.n_eq = s->n_eq; h.n_ic = s->has_ic ? s->n_ic : 0; h.n_slots = s->n_slots;
     h.bc = s->bc_value;
     h.ic_has_vars = (s->has_ic && s->ic_has_vars) ? 1 : 0;

@@ -22,6 +22,7 @@
 #include "pinn_step_kernel.cuh"
 #include "pinn_wide_kernel.cuh"
 #include "pinn_small_kernel.cuh"
+#include "pinn_hi_kernel.cuh"
 #include "pinn_host_plan.h"
 
 // small_step_kernel instantiations live in pinn_small_nf*.cu
@@ -215,7 +216,15 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         int rc = build_dev_plan(s, p->h, p->fwd_rows, p->fwd_row_scr, msg, sizeof(msg));
         if (rc) { delete p; return fail(rc, "%s", msg); }
     }
-    if (!find_variant(s->nf, s->ns, p->var_store)) {
+    const int order = spec_order(s);
+    if (order >= 3) {
+        // derivatives of order 3 / 4: whole jets per direction (pinn_hi_kernel.cuh), one kernel per (nf, order)
+        StepKernelFn f = s->nf == 1 ? pinn_hi_variant_nf1(order) : s->nf == 2 ? pinn_hi_variant_nf2(order)
+                       : s->nf == 3 ? pinn_hi_variant_nf3(order) : nullptr;
+        if (!f) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel for derivative order %d with %d directions", order, s->nf); }
+        const Variant v = {s->nf, 0, nullptr, nullptr, nullptr, f, nullptr, 256};
+        p->var_store = v;
+    } else if (!find_variant(s->nf, s->ns, p->var_store)) {
         delete p;
         return fail(PINN_E_UNSUPPORTED, "no kernel variant for nf=%d ns=%d%s", s->nf, s->ns,
                     s->nf > 4 ? " (more than 4 derivative directions: every direction must carry its second derivative, ns = nf)" : "");
@@ -335,7 +344,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     // ---- tiny batches: the (point, unit)-parallel loop kernel; plain dense chains whose jets fit shared memory ----
     {
         p->fn_small = nullptr; p->small_smem = 0;
-        bool plain = s->nf <= 4;
+        bool plain = s->nf <= 4 && order < 3;
         for (int l = 0; l < h.n_layers; ++l) if (h.layer[l].skip_src >= 0 || h.layer[l].post_base >= 0) plain = false;
         if (plain) {
             MultiKernelFn f = nullptr;
@@ -361,7 +370,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
         p->wide = false; p->fn_wide = nullptr; p->wide_ctas = p->sm_count;
         int mw = 0;
         const char* fk = getenv("PINN_FORCE_KERNEL");
-        const bool eligible = wide_eligible(h, &mw);
+        const bool eligible = order < 3 && wide_eligible(h, &mw);
         // measured on B200: the tile kernel wins from 64-wide layers with many jet channels on (cfg5: 13.6 ms vs
         // 15.3 ms); for 30-40-wide networks the CUDA-core kernel is several times faster (cfg4: 2.6 ms vs 9.3 ms) —
         // per (unit, channel) operand handling costs as much as a 64-long FMA row
@@ -828,7 +837,7 @@ extern "C" int pinn_record_loss(const PinnPlan* p, const float* grads_and_loss, 
 
 extern "C" int pinn_plan_info(const PinnPlan* p, PinnPlanInfo* info) {
     if (!p || !info) return fail(PINN_E_INVALID, "null argument");
-    const int C = 1 + p->h.nf + p->h.ns;
+    const int C = spec_channels(&p->spec);
     long long macs = 0;
     for (int l = 0; l < p->h.n_layers; ++l) macs += (long long)p->h.layer[l].n_in * p->h.layer[l].n_out;
     info->nf = p->h.nf; info->ns = p->h.ns; info->channels = C;

@@ -75,6 +75,7 @@ def const(v):
 
 
 ZERO, ONE = const(0.0), const(1.0)
+MAX_ORDER = 4                               # D() nests up to four times on the fused path (u_xxx of KdV, u_xxxx of beams)
 
 
 def is_const(e, v=None):
@@ -266,8 +267,8 @@ def diff_coord(e, k, memo=None):
     elif e.kind == 'coord':
         r = ONE if e.value == k else ZERO
     elif e.kind == 'u':
-        if len(e.value) >= 2:
-            raise NotLowerable('derivatives of order > 2 are not supported by the fused path')
+        if len(e.value) >= MAX_ORDER:
+            raise NotLowerable('derivatives of order > %d are not supported by the fused path' % MAX_ORDER)
         r = uleaf(e.value + (k,))
     else:
         r = _chain(e, lambda a: diff_coord(a, k, memo))
@@ -650,6 +651,8 @@ class TracedEquation:
         self.ic_prog = None         # outputs: jet of ic (C entries) [+ C partials per variable] or None
         self.ic_has_vars = False
         self.n_slots = 0
+        self.order = 2              # 3 / 4: every direction carries its whole Taylor jet up to this order (ns = 0):
+                                    # channel 1 + d*order + (k-1) = k-th derivative along direction d
 
     @property
     def nf(self):
@@ -657,7 +660,7 @@ class TracedEquation:
 
     @property
     def channels(self):
-        return 1 + self.nf + self.ns
+        return 1 + self.nf * self.order if self.order > 2 else 1 + self.nf + self.ns
 
 
 def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0, run=None):
@@ -676,6 +679,8 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
     T.residual = res
 
     u_leaves = leaves(res, ('u',))
+    if any(len(l.value) > 2 for l in u_leaves):
+        return _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run)
     first, second, mixed = set(), set(), set()
     for l in u_leaves:
         mi = l.value
@@ -756,6 +761,62 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
             jet = jet + [diff_leaf(j, var(n)) for n in T.var_names for j in jet]
             base = T.eq_prog.n_slots
         T.ic_prog = lower(jet, {}, var_index, base)
+        T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
+    return T
+
+
+def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run):
+    """ Equations with derivatives of order 3 / 4 (D nested three / four times along ONE argument: u_xxx, u_xxxx):
+    every differentiated axis carries its whole Taylor jet up to the highest order met (pinn_device_hi.cuh). """
+    order = max(len(l.value) for l in u_leaves)
+    axes = set()
+    for l in u_leaves:
+        if len(set(l.value)) > 1:
+            raise NotLowerable('mixed derivatives next to derivatives of order > 2')
+        axes.update(l.value)
+    axes = sorted(axes)
+    nf = len(axes)
+    if nf > 3:
+        raise NotLowerable('derivatives of order > 2 along more than 3 arguments')
+
+    def unit(k):
+        return [1.0 if i == k else 0.0 for i in range(total)]
+    T.order, T.ns = order, 0
+    T.dirs, T.dir_vecs = list(axes), [unit(k) for k in axes]
+    C = 1 + nf * order
+    mapping = {uleaf(): chleaf(0)}
+    for d, col in enumerate(axes):
+        for n in range(1, order + 1):
+            mapping[uleaf((col,) * n)] = chleaf(1 + d * order + (n - 1))
+    res = substitute(res, mapping)
+    T.residual = res
+
+    ic = None
+    if initial_condition is not None:
+        if callable(initial_condition):
+            ic_out = run(initial_condition, *xs[:ndims_spatial])
+            ic = ic_out.expr if isinstance(ic_out, Sym) else _as_expr(ic_out)
+        else:
+            ic = const(float(np.float32(initial_condition)))
+        if leaves(ic, ('u',)):
+            raise NotLowerable('initial_condition must not depend on the solution')
+        if leaves(ic, ('var',)):
+            raise NotLowerable('variables inside the initial condition next to derivatives of order > 2')
+    T.var_names = sorted({l.value for l in leaves(res, ('var',))})
+    if len(T.var_names) > 4:
+        raise NotLowerable('more than 4 trainable variables')
+    var_index = {n: i for i, n in enumerate(T.var_names)}
+    outputs = [res] + [diff_leaf(res, chleaf(c)) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
+    T.eq_prog = lower(outputs, {}, var_index, C)
+    T.n_slots = T.eq_prog.n_slots
+    if ic is not None:
+        jet = [ic]
+        for col in axes:
+            e = ic
+            for _ in range(order):
+                e = diff_coord(e, col)
+                jet.append(e)
+        T.ic_prog = lower(jet, {}, var_index, C)
         T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
     return T
 

@@ -12,6 +12,7 @@
 #include <limits>
 #include <string.h>
 #include "../../pydens_b200/csrc/pinn_host_plan.h"
+#include "../../pydens_b200/csrc/pinn_device_hi.cuh"
 
 using namespace pinn;
 
@@ -54,6 +55,31 @@ static void run_step(const DevPlan& P, const float* sw, const float* params, con
     for (int i = 0; i < P.n_vars; ++i) out[P.var_off[i]] += part.vbar[i];
 }
 
+// derivatives of order 3 / 4: the whole-jet code of pinn_device_hi.cuh, driven the same way
+template <int NF, int K>
+static void run_step_hi(const DevPlan& P, const float* sw, const float* params, const float* points, long long n,
+                        float inv_n, float* out, float* residual) {
+    std::vector<float> st = poisoned_rows(P.rows_total);
+    GradSink sink;
+    sink.wacc = out;
+    sink.atomic = false;
+    sink.dump = P.n_params + 2;
+    hi::PartialsHi part;
+    part.loss = 0.0f; part.sbar = 0.0f;
+    for (int i = 0; i < PINN_MAX_VARS; ++i) part.vbar[i] = 0.0f;
+    for (long long p = 0; p < n; ++p) {
+        float* lane = st.data() + (p % EMUL_RS);
+        for (int r = 0; r < P.rows_total; ++r) lane[(size_t)r * EMUL_RS] = EMUL_STALE;
+        for (int k = 0; k < P.total; ++k) lane[(size_t)k * EMUL_RS] = points[p * P.total + k];
+        float r = hi::point_step<NF, K>(P, sw, params, lane, EMUL_RS, true, inv_n, sink, part);
+        for (int q = 0; q < P.rows_total; ++q) lane[(size_t)q * EMUL_RS] = std::numeric_limits<float>::quiet_NaN();
+        if (residual) residual[p] = r;
+    }
+    out[P.n_params] += part.loss;
+    out[P.log_scale_off] += part.sbar;
+    for (int i = 0; i < P.n_vars; ++i) out[P.var_off[i]] += part.vbar[i];
+}
+
 extern "C" int emul_step(const PinnSpec* spec, const float* params, const float* points, long long n, float inv_n,
                          float* out, float* residual, char* msg, int msg_len) {
     DevPlan P;
@@ -63,6 +89,10 @@ extern "C" int emul_step(const PinnSpec* spec, const float* params, const float*
     std::vector<float> sw(P.weights_floats + 16);
     host_stage_weights(P, params, sw.data());
     for (int i = 0; i < P.n_params + 4; ++i) out[i] = 0.0f;
+#define CASE_HI(NF_, K_) if (spec_order(spec) == K_ && P.nf == NF_) { run_step_hi<NF_, K_>(P, sw.data(), params, points, n, inv_n, out, residual); return 0; }
+    CASE_HI(1, 3) CASE_HI(2, 3) CASE_HI(3, 3) CASE_HI(1, 4) CASE_HI(2, 4) CASE_HI(3, 4)
+#undef CASE_HI
+    if (spec_order(spec) >= 3) { snprintf(msg, msg_len, "no hi variant nf=%d order=%d", P.nf, spec_order(spec)); return PINN_E_UNSUPPORTED; }
 #define CASE(NF_, NS_) if (P.nf == NF_ && P.ns == NS_) { run_step<NF_, NS_>(P, sw.data(), params, points, n, inv_n, out, residual); return 0; }
     CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2)
     CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)

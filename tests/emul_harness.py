@@ -14,7 +14,7 @@ import problems as P
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'emul', 'pinn_emul.cpp')
 LIB = os.path.join(HERE, 'emul', 'libpinn_emul.so')
-DEPS = [SRC] + [os.path.join(HERE, '..', 'pydens_b200', 'csrc', f) for f in ('pinn_device.cuh', 'pinn_host_plan.h')] \
+DEPS = [SRC] + [os.path.join(HERE, '..', 'pydens_b200', 'csrc', f) for f in ('pinn_device.cuh', 'pinn_device_hi.cuh', 'pinn_host_plan.h')] \
     + [os.path.join(HERE, '..', 'include', 'pinn_b200.h')]
 _lib = None
 

@@ -32,10 +32,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / 'sz.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pinn_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PinnSpec), sizeof(PinnInstr),'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PinnSpec), sizeof(PinnInstr),'
                    ' sizeof(PinnColumn), sizeof(PinnPlanInfo), offsetof(PinnSpec, eq_prog), offsetof(PinnSpec, ic_out),'
                    ' offsetof(PinnSpec, n_slots), sizeof(PinnAdam), offsetof(PinnAdam, lr), offsetof(PinnAdam, losses_ring),'
-                   ' offsetof(PinnPlanInfo, small_batch_points));return 0;}\n')
+                   ' offsetof(PinnPlanInfo, small_batch_points), offsetof(PinnSpec, order));return 0;}\n')
     exe = tmp_path / 'sz'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     got = list(map(int, subprocess.check_output([str(exe)]).split()))
@@ -43,7 +43,7 @@ def test_struct_layout_matches_c(tmp_path):
     assert got == [C.sizeof(S), C.sizeof(_native.PinnInstr), C.sizeof(_native.PinnColumn),
                    C.sizeof(_native.PinnPlanInfo), S.eq_prog.offset, S.ic_out.offset, S.n_slots.offset,
                    C.sizeof(_native.PinnAdam), _native.PinnAdam.lr.offset, _native.PinnAdam.losses_ring.offset,
-                   _native.PinnPlanInfo.small_batch_points.offset]
+                   _native.PinnPlanInfo.small_batch_points.offset, S.order.offset]
 
 
 def test_plan_create_rejects_bad_spec_without_gpu():

@@ -41,7 +41,7 @@ def test_fused_backend_raises_without_gpu_or_lowering():
     with pytest.raises(RuntimeError):
         solver.fit(niters=1, batch_size=10)
     with pytest.raises(RuntimeError):
-        Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu', backend='fused')
+        Solver(lambda f, x: D(D(D(D(D(f, x), x), x), x), x), ndims=1, device='cpu', backend='fused')     # fifth order
 
 
 def test_reshape_and_concat_contract():
@@ -76,7 +76,9 @@ def test_variables_constraints_and_freezing():
 
 
 def test_lowering_decisions():
-    assert Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu')._traced is None
+    s = Solver(lambda f, x: D(D(D(f, x), x), x), ndims=1, device='cpu')
+    assert s._traced is not None and s._traced.order == 3                         # whole-jet kernels (orders 3 and 4)
+    assert Solver(lambda f, x: D(D(D(D(D(f, x), x), x), x), x), ndims=1, device='cpu')._traced is None
     s = Solver(lambda f, x, y: D(D(f, x), y), ndims=2, device='cpu')
     assert s._traced is not None and s._traced.dirs == [0, 1, -1]                 # mixed derivative: polarised
     s = Solver(lambda f, x, y, z: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z), ndims=3, device='cpu')

@@ -10,17 +10,41 @@ import emul_harness as E
 from helpers import load_golden, oracle_problem, rel_l2
 
 
+def reference_fp32_error(name, g):
+    """ How far the reference's own fp32 numbers (the golden) are from the fp64 oracle: (residual, gradient) rel-L2.
+    Nested autograd of order 3 / 4 in fp32 loses digits (the beam problem's golden residual is 1.1e-4 off), so for
+    those problems a comparison against the golden carries this much slack on top of the stated tolerance. """
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    _, r64, g64 = prob.loss_and_grads(g['points'].astype(np.float64))
+    return rel_l2(g['residual'], r64), rel_l2(g['grads'], g64.numpy())
+
+
 @pytest.mark.parametrize('name', list(P.PROBLEMS))
 def test_device_math_matches_reference(name):
     g = load_golden(name)
     spec = E.spec_for(name)
     assert spec.n_params == g['params'].size
     loss, residual, grads = E.emul_step(spec, g['params'], g['points'])
-    assert abs(loss - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))          # fp32 tolerance
-    assert rel_l2(residual, g['residual']) <= 1e-5
-    assert rel_l2(grads, g['grads']) <= 1e-4
+    slack_r, slack_g = reference_fp32_error(name, g) if name in P.HI_ORDER else (0.0, 0.0)
+    assert abs(loss - float(g['loss'])) <= (1e-5 + 2.0 * slack_r) * abs(float(g['loss']))          # fp32 tolerance
+    assert rel_l2(residual, g['residual']) <= 1e-5 + 1.5 * slack_r
+    assert rel_l2(grads, g['grads']) <= 1e-4 + 1.5 * slack_g
     u = E.emul_forward(spec, g['params'], g['points'])
     assert rel_l2(u, g['u']) <= 1e-5
+
+
+@pytest.mark.parametrize('name', list(P.HI_ORDER))
+def test_high_order_device_math_is_closer_to_fp64_than_the_reference(name):
+    """ Orders 3 / 4: the arbiter is the fp64 oracle; the hand-derived jets must be at least as close to it as the
+    reference's fp32 nested autograd, and inside the stated fp32 tolerances in any case. """
+    g = load_golden(name)
+    spec = E.spec_for(name)
+    _, residual, grads = E.emul_step(spec, g['params'], g['points'])
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    _, r64, g64 = prob.loss_and_grads(g['points'].astype(np.float64))
+    ref_r, ref_g = reference_fp32_error(name, g)
+    assert rel_l2(residual, r64) <= max(2.0 * ref_r, 1e-6) and rel_l2(residual, r64) <= 1e-5
+    assert rel_l2(grads, g64.numpy()) <= max(2.0 * ref_g, 1e-6) and rel_l2(grads, g64.numpy()) <= 1e-4
 
 
 @pytest.mark.parametrize('name', ['poisson2d', 'heat2d', 'burgers', 'ode_var', 'poisson_sin', 'heat_softplus', 'burgers_silu',
@@ -33,6 +57,49 @@ def test_device_math_vs_fp64(name):
     _, _, g64 = prob.loss_and_grads(g['points'].astype(np.float64))
     ours, ref = rel_l2(grads, g64.numpy()), rel_l2(g['grads'], g64.numpy())
     assert ours <= max(4 * ref, 1e-6)           # no worse than the reference's own fp32 error
+
+
+@pytest.mark.parametrize('name', [n for n in P.GOLDEN_TRAJ if n in P.HI_ORDER + P.HI_DIRECTION] + ['poisson2d', 'burgers'])
+def test_emulated_fit_follows_the_reference_fit(name):
+    """ The whole loop on the CPU: device math (host build) for loss and gradients, the oracle's Adam restatement for
+    optimizer.step(), on the batches the reference's own Solver.fit saw (golden trajectory) — the tolerances the GPU
+    trajectory tests apply to the kernels. """
+    from oracle.adam import adam_step
+    g = load_golden(name)
+    niters, batch, lr = int(g['traj_meta'][0]), int(g['traj_meta'][1]), float(g['traj_meta'][2])
+    spec = E.spec_for(name)
+    params = g['params'].astype(np.float32).copy()
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    losses = []
+    for i in range(niters):
+        loss, _, grads = E.emul_step(spec, params, P.make_points(name, batch, seed=1000 + i))
+        losses.append(loss)
+        adam_step(params, grads, m, v, i + 1, lr=lr)
+    losses, ref = np.asarray(losses, dtype=np.float64), g['traj_losses'].astype(np.float64)
+    assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-3
+    assert abs(losses[-1] - ref[-1]) <= 1e-5 * max(1.0, abs(ref[-1]))
+    assert np.linalg.norm(params - g['traj_params']) / np.linalg.norm(g['traj_params']) <= 1e-3
+
+
+def test_fourth_order_sigmoid_fit_follows_fp64_where_the_reference_does_not():
+    """ The beam problem (u_tt + u_xxxx, sigmoid network): along an Adam fit the hand-derived jets stay within fp32
+    rounding of the fp64 oracle at every step.  (The reference's fp32 nested autograd does not: recorded with
+    oracle/make_golden.py it returned losses of 1.78 and 921.7 at steps 9 and 12 of this very fit, where fp64 gives
+    0.177 and 0.169 — which is why this problem has no golden trajectory.) """
+    from oracle.adam import adam_step
+    name = 'beam'
+    g = load_golden(name)
+    spec = E.spec_for(name)
+    params = g['params'].astype(np.float32).copy()
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    for i in range(15):
+        pts = P.make_points(name, 40, seed=1000 + i)
+        loss, _, grads = E.emul_step(spec, params, pts)
+        prob = oracle_problem(name, torch.float64, params.astype(np.float64))
+        l64, _, g64 = prob.loss_and_grads(pts.astype(np.float64))
+        assert abs(loss - l64) <= 1e-5 * abs(l64), i
+        assert rel_l2(grads, g64.numpy()) <= 1e-4, i
+        adam_step(params, grads, m, v, i + 1, lr=0.01)
 
 
 def test_per_tensor_gradients_poisson():

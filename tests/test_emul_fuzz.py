@@ -219,3 +219,90 @@ def test_random_many_direction_problem_matches_fp64_oracle(seed):
     u = E.emul_forward(spec, params.astype(np.float32), pts)
     ref_u = prob.predict(pts.astype(np.float64))
     assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# derivatives of order 3 / 4 (kernels hi_step_kernel<NF, K>: every direction carries its whole Taylor jet)
+# ---------------------------------------------------------------------------------------------------------------
+def _high_order_equations(ndims):
+    D3 = lambda D, u, x: D(D(D(u, x), x), x)
+    D4 = lambda D, u, x: D(D(D(D(u, x), x), x), x)
+    eqs = [('ode3', lambda u, *xs, D, V: D3(D, u, xs[0]) + D(u, xs[0]) * u - torch.cos(xs[0])),
+           ('ode4', lambda u, *xs, D, V: D4(D, u, xs[0]) - 2.0 * D(D(u, xs[0]), xs[0]) + u ** 2 - xs[0]),
+           ('ode3var', lambda u, *xs, D, V: D3(D, u, xs[0]) * V('k', 0.7) + D(D(u, xs[0]), xs[0]) - V('k', 0.7) * torch.sin(u))]
+    if ndims >= 2:
+        j = ndims - 1
+        eqs += [('kdv', lambda u, *xs, D, V: D(u, xs[j]) + 6.0 * u * D(u, xs[0]) + D3(D, u, xs[0])),
+                ('beam', lambda u, *xs, D, V: D(D(u, xs[j]), xs[j]) + 0.5 * D4(D, u, xs[0]) - torch.sin(xs[0])),
+                ('ks', lambda u, *xs, D, V: D(u, xs[j]) + u * D(u, xs[0]) + D(D(u, xs[0]), xs[0]) + D4(D, u, xs[0])),
+                ('third_in_time', lambda u, *xs, D, V: D3(D, u, xs[j]) + D(D(u, xs[0]), xs[0]) * xs[j] - u)]
+    if ndims >= 3:
+        eqs += [('plate', lambda u, *xs, D, V: D(D(u, xs[2]), xs[2]) + 0.1 * (D4(D, u, xs[0]) + D4(D, u, xs[1])) + D3(D, u, xs[0]) * u),
+                ('three3', lambda u, *xs, D, V: D3(D, u, xs[0]) + D3(D, u, xs[1]) - D(u, xs[2]) + xs[1] * D(D(u, xs[0]), xs[0]))]
+    return eqs
+
+
+def _random_high_order_problem(seed):
+    rng = np.random.RandomState(90000 + seed)
+    ndims = int(rng.randint(1, 4))
+    nparams = int(rng.randint(0, 2)) if ndims < 3 else 0
+    total = ndims + nparams
+    depth = int(rng.randint(1, 4))                               # hidden layers (the oracle's nested autograd needs one)
+    widths = [int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 23])) for _ in range(depth)]
+    acts = [['Tanh', 'Sigmoid'][int(rng.randint(2))] for _ in range(depth)]
+    eqs = _high_order_equations(ndims)
+    name, eq = eqs[int(rng.randint(len(eqs)))]
+    has_ic = ndims >= 2 and bool(rng.rand() < 0.6)
+    if name in ('ode3', 'ode4', 'ode3var') and ndims == 1:
+        has_ic = bool(rng.rand() < 0.4)
+    nsp = ndims - 1 if has_ic else ndims
+    ic = None
+    if has_ic:
+        if nsp == 0 or rng.rand() < 0.3:
+            ic = float(np.round(rng.uniform(-1, 2), 2))
+        elif rng.rand() < 0.5:
+            ic = lambda *x: torch.sin(2.0 * x[0]) + 0.5
+        else:
+            ic = lambda *x: x[0] * (1.0 - x[-1]) * x[0] + 0.25 * torch.exp(-x[-1])
+    bc = float(np.round(rng.uniform(-1, 1), 2)) if (nsp > 0 and rng.rand() < 0.6) else None
+    domain = [(float(np.round(rng.uniform(-1, 0.2), 2)), float(np.round(rng.uniform(0.8, 2.5), 2))) for _ in range(ndims)]
+    return dict(ndims=ndims, nparams=nparams, total=total, features=widths + [1], acts=acts, layout='fa' * depth + 'f', ic=ic, bc=bc,
+                domain=domain, eq=eq, eq_name=name, ranges=domain + [(0.5, 2.0)] * nparams,
+                variables={'k': 0.7} if name == 'ode3var' else None, log_scale=float(np.round(rng.uniform(-0.5, 0.5), 2)))
+
+
+@pytest.mark.parametrize('seed', list(range(60)))
+def test_random_high_order_problem_matches_fp64_oracle(seed):
+    cfg = _random_high_order_problem(seed)
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    nsp = cfg['ndims'] - 1 if cfg['ic'] is not None else cfg['ndims']
+    traced = T.trace(lambda u, *xs: cfg['eq'](u, *xs, D=T.sym_D, V=sym_V), cfg['total'], None,
+                     initial_condition=cfg['ic'], ndims_spatial=nsp)
+    assert traced.order in (3, 4) and traced.ns == 0 and traced.channels == 1 + traced.nf * traced.order, cfg['eq_name']
+    acts, skips = _layer_plan(cfg)
+    spec = N.build_spec([cfg['total']] + cfg['features'], acts, cfg['ndims'], cfg['nparams'], cfg['bc'] is not None,
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, cfg['ic'] is not None, cfg['domain'], traced,
+                        skips=skips)
+    assert spec.order == traced.order
+    prob = ap.Problem(cfg['eq'], ndims=cfg['ndims'], nparams=cfg['nparams'], initial_condition=cfg['ic'],
+                      boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
+                      activation=cfg['acts'] or 'Tanh', dtype=torch.float64, variables=cfg['variables'], seed=seed,
+                      layout=cfg['layout'])
+    with torch.no_grad():
+        prob.log_scale.fill_(cfg['log_scale'])
+    params = prob.flat_params().numpy()
+    assert spec.n_params == params.size
+    rng = np.random.RandomState(4000 + seed)
+    n = int(rng.choice([1, 7, 33, 64]))
+    pts = np.concatenate([rng.uniform(lo, hi, size=(n, 1)) for lo, hi in cfg['ranges']], axis=1).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params.astype(np.float32), pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float32).astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    tag = '%s %s %s acts=%s' % (cfg['eq_name'], cfg['layout'], cfg['features'], acts)
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 2e-5 * cond * max(abs(ref_loss), 1e-6), tag
+    assert rel_l2(residual, ref_res) <= 2e-5 * cond, tag
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, tag
+    u = E.emul_forward(spec, params.astype(np.float32), pts)
+    ref_u = prob.predict(pts.astype(np.float64))
+    assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag

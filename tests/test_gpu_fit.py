@@ -17,7 +17,7 @@ if torch.cuda.is_available():
 
 
 @pytest.mark.parametrize('adam', ['kernel', 'torch'])
-@pytest.mark.parametrize('name', [n for n in P.GOLDEN_TRAJ if n not in P.HI_DIRECTION])
+@pytest.mark.parametrize('name', [n for n in P.GOLDEN_TRAJ if n not in P.HI_DIRECTION + P.HI_ORDER])
 def test_fit_trajectory_matches_reference_fit(name, adam, monkeypatch):
     """ Same init, same point stream, same Adam: the loss curve of the fused fit follows the curve of the
     reference's `Solver.fit` (BASELINE: residual MSE within 1e-5 of reference on identical points).  Both forms of

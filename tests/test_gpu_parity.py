@@ -17,7 +17,7 @@ if torch.cuda.is_available():
 
 
 # (the problems with five / six derivative directions have their own file, test_gpu_zz_directions.py)
-@pytest.mark.parametrize('name', [n for n in P.PROBLEMS if n not in P.HI_DIRECTION])
+@pytest.mark.parametrize('name', [n for n in P.PROBLEMS if n not in P.HI_DIRECTION + P.HI_ORDER])
 def test_step_matches_reference_golden(name):
     g = load_golden(name)
     solver = make_solver(name, g['params'])

@@ -85,8 +85,12 @@ def test_ic_program_is_the_jet_of_ic():
 
 def test_not_lowerable_cases():
     D = T.sym_D
-    with pytest.raises(T.NotLowerable):            # third order
-        T.trace(lambda f, x: D(D(D(f, x), x), x), 1, None)
+    with pytest.raises(T.NotLowerable):            # fifth order
+        T.trace(lambda f, x: D(D(D(D(D(f, x), x), x), x), x), 1, None)
+    with pytest.raises(T.NotLowerable):            # a mixed derivative next to a third-order one
+        T.trace(lambda f, x, y: D(D(D(f, x), x), x) + D(D(f, x), y), 2, None)
+    with pytest.raises(T.NotLowerable):            # third-order mixed derivative
+        T.trace(lambda f, x, y: D(D(D(f, x), x), y), 2, None)
     with pytest.raises(T.NotLowerable):            # more than 6 directions (3 axes + 3 diagonals + t)
         T.trace(lambda f, x, y, z, t: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z) + D(f, t), 4, None)
     with pytest.raises(T.NotLowerable):            # data-dependent branch
@@ -113,6 +117,34 @@ def test_five_and_six_directions_are_promoted_to_second_order():
     outs = T.run_program(tr.eq_prog, jet, coords, [])
     assert np.all(outs[1 + 10] == 0.0) and np.allclose(outs[1 + 5], -coords[4])
     np.testing.assert_allclose(outs[0], jet[6] + jet[7] + jet[8] + jet[9] - jet[5] * coords[4], rtol=1e-12)
+
+
+def test_third_and_fourth_order_derivatives_carry_whole_jets():
+    """ D nested three / four times along one argument: every differentiated axis carries its Taylor jet up to the
+    highest order met; channel 1 + d*order + (k-1) = k-th derivative along direction d. """
+    D = T.sym_D
+    tr = T.trace(lambda u, x, t: D(u, t) + 6.0 * u * D(u, x) + D(D(D(u, x), x), x), 2, None,
+                 initial_condition=lambda x: torch.sin(2.0 * x), ndims_spatial=1)
+    assert (tr.order, tr.nf, tr.ns, tr.dirs, tr.channels) == (3, 2, 0, [0, 1], 7)
+    rng = np.random.RandomState(1)
+    coords, jet = rng.uniform(0.2, 0.9, size=(2, 5)), rng.normal(size=(7, 5))
+    outs = T.run_program(tr.eq_prog, jet, coords, [])
+    # channels: 0 u | 1 u_x, 2 u_xx, 3 u_xxx | 4 u_t, 5 u_tt, 6 u_ttt
+    np.testing.assert_allclose(outs[0], jet[4] + 6.0 * jet[0] * jet[1] + jet[3], rtol=1e-12)
+    np.testing.assert_allclose(outs[1 + 0], 6.0 * jet[1], rtol=1e-12)
+    np.testing.assert_allclose(outs[1 + 1], 6.0 * jet[0], rtol=1e-12)
+    assert np.all(outs[1 + 3] == 1.0) and np.all(outs[1 + 4] == 1.0) and np.all(outs[1 + 2] == 0.0) and np.all(outs[1 + 6] == 0.0)
+    ic = T.run_program(tr.ic_prog, np.zeros((7, 5)), coords, [])
+    x = coords[0]
+    np.testing.assert_allclose(ic[0], np.sin(2 * x), rtol=1e-12)
+    np.testing.assert_allclose(ic[1], 2 * np.cos(2 * x), rtol=1e-12)
+    np.testing.assert_allclose(ic[3], -8 * np.cos(2 * x), rtol=1e-12)
+    assert np.all(ic[4] == 0.0) and np.all(ic[6] == 0.0)            # the initial condition does not depend on t
+    tr = T.trace(lambda u, x, t: D(D(u, t), t) + D(D(D(D(u, x), x), x), x) * T.Sym(T.var('q')), 2, None)
+    assert (tr.order, tr.channels, tr.var_names) == (4, 9, ['q'])
+    with pytest.raises(T.NotLowerable):            # variables inside the initial condition stay on the order-2 path
+        T.trace(lambda u, x, t: D(D(D(u, x), x), x) + D(u, t), 2, None,
+                initial_condition=lambda x: x * T.Sym(T.var('amp')), ndims_spatial=1)
 
 
 def test_variables_inside_initial_condition():
