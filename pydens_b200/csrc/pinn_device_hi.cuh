@@ -12,8 +12,8 @@
 // transposed product, including d/d log_scale through the time gate.
 //
 // Written per THREAD like pinn_device.cuh and `__host__ __device__` for the same reason: tests/emul compiles these
-// very functions with g++ and checks them against the fp64 oracle.  Scope: plain dense chains, tanh / sigmoid (and
-// the linear last layer), axis-aligned directions, no variables inside the initial condition — everything else about
+// very functions with g++ and checks them against the fp64 oracle.  Scope: plain dense chains, tanh / sigmoid / sin
+// (and the linear last layer), axis-aligned directions, no variables inside the initial condition — everything else about
 // a problem (samplers, variables in the equation, domains, boundary / initial conditions) is as in the main path.
 // This path favours clarity over the last FMA: it exists so that such equations stay on the GPU in one launch
 // instead of falling back to nested autograd graphs.
@@ -47,12 +47,24 @@ PINN_HD void act_derivs(int act, float a, float (&s)[K + 2]) {
         s[3] = s1 * fmaf(fmaf(6.0f, a, -6.0f), a, 1.0f);
         s[4] = s1 * fmaf(fmaf(fmaf(-24.0f, a, 36.0f), a, -14.0f), a, 1.0f);
         if (K + 1 >= 5) s[K + 1 >= 5 ? 5 : 0] = s1 * fmaf(fmaf(fmaf(fmaf(120.0f, a, -240.0f), a, 150.0f), a, -30.0f), a, 1.0f);
+    } else if (act == PINN_ACT_SIN) {                     // z-stored: `a` is the pre-activation z itself
+        float sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincosf(a, &sn, &cs);
+#else
+        sn = sinf(a); cs = cosf(a);
+#endif
+        s[1] = cs; s[2] = -sn; s[3] = -cs; s[4] = sn;
+        if (K + 1 >= 5) s[K + 1 >= 5 ? 5 : 0] = cs;
     } else {
         s[1] = 1.0f;
 #pragma unroll
         for (int k = 2; k <= K + 1; ++k) s[k] = 0.0f;
     }
 }
+
+// value of a hidden unit from what its row stores (tanh / sigmoid / identity store the value, sin stores z)
+PINN_HD float act_value(int act, float stored) { return act == PINN_ACT_SIN ? sinf(stored) : stored; }
 
 // Post-activation jet of one direction from its pre-activation jet z[1..K] (index 0 unused).
 template <int K>
@@ -107,7 +119,7 @@ PINN_HD void load_post(const float* __restrict__ row, int RS, int act, float (&p
     const float a = row[0];
     float s[K + 2];
     act_derivs<K>(act, a, s);
-    p[0] = a;
+    p[0] = act_value(act, a);
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
         float z[K + 1], q[K + 1];
