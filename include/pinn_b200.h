@@ -191,8 +191,9 @@ typedef struct PinnSpec {
                                    3 or 4 (D nested three / four times, model_torch.py:174-178: u_xxx of KdV, u_xxxx of beam
                                    equations): EVERY direction carries its Taylor jet up to this order — channel
                                    1 + d*order + (k-1) holds the k-th derivative along direction d, channels = 1 + nf*order;
-                                   ns is ignored (0); nf <= 3, axis-aligned directions (dir_col[d] >= 0), plain dense chains
-                                   with tanh / sigmoid, no variables inside the initial condition */
+                                   ns is ignored (0); nf <= 4 (axes, and diagonals e_i +- e_j that carry mixed derivatives by
+                                   polarisation), plain dense chains with tanh / sigmoid / sin, no variables inside the
+                                   initial condition */
 } PinnSpec;
 
 typedef struct PinnPlan PinnPlan;

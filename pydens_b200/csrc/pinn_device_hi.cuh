@@ -157,7 +157,7 @@ PINN_HD void fwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, co
             for (int c = 1; c < C; ++c) acc[q][c] = 0.0f;
         }
         if (l == 0) {
-            // input jet of coordinate k: (x_k; 1 along its own axis at first order; nothing above)
+            // input jet of coordinate k along direction v: (x_k; v_k at first order; nothing above)
 #pragma unroll 1
             for (int k = 0; k < L.n_in; ++k) {
                 const float4 w = *reinterpret_cast<const float4*>(Wt + (size_t)k * L.n_out_p4 + j0);
@@ -168,7 +168,7 @@ PINN_HD void fwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, co
                     acc[q][0] = fmaf(wq[q], x, acc[q][0]);
 #pragma unroll
                     for (int d = 0; d < NF; ++d)
-                        if (P.dir_col[d] == k) acc[q][chan(K, d, 1)] += wq[q];
+                        acc[q][chan(K, d, 1)] = fmaf(wq[q], P.dir_vec[d][k], acc[q][chan(K, d, 1)]);
                 }
             }
         } else {
@@ -212,7 +212,7 @@ PINN_HD void fwd_final(const DevPlan& P, const float* __restrict__ sw, const flo
             N[0] = fmaf(w[k], coords[(size_t)k * RS], N[0]);
 #pragma unroll
             for (int d = 0; d < NF; ++d)
-                if (P.dir_col[d] == k) N[chan(K, d, 1)] += w[k];
+                N[chan(K, d, 1)] = fmaf(w[k], P.dir_vec[d][k], N[chan(K, d, 1)]);
         }
     } else {
         const float* in_rows = units + (size_t)P.layer[Ln - 2].unit_base * C * RS;
@@ -230,9 +230,9 @@ PINN_HD void fwd_final(const DevPlan& P, const float* __restrict__ sw, const flo
 
 // ---------------------------------------------------------------------------------------------------------------
 // Ansatz (model_torch.py:107-128) as products of jets:  v = bc + G N,  u = S v + ic
-//   G = prod_i q_i(x_i), q_i = (x - lo)(hi - x) / w^2 over the spatial dims: along a spatial axis its jet is
-//       (G, others q', others q'', 0, 0);  constant along every other direction
-//   S = sigmoid(y) - 1/2, y = (t - t0) / exp(log_scale): along the time axis its jet is sigmoid^(k)(y) / s^k
+//   G = prod_i q_i(x_i), q_i = (x - lo)(hi - x) / w^2 over the spatial dims: along a direction v its jet is the product
+//       of the jets (q_i, q_i' v_i, q_i'' v_i^2, 0, 0)
+//   S = sigmoid(y) - 1/2, y = (t - t0) / exp(log_scale): along v its jet is sigmoid^(k)(y) (v_t / s)^k
 // ---------------------------------------------------------------------------------------------------------------
 PINN_HD float binom(int n, int k) {
     const float tab[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
@@ -243,16 +243,54 @@ template <int NF, int K>
 struct AnsatzHi {
     float G, Gj[NF][K + 1];            // boundary factor and its jet per direction (Gj[d][0] = G)
     float Sg, Sj[NF][K + 1];           // time gate and its jet per direction
-    float dS[K + 1];                   // d Sj[time][k] / d log_scale (k = 0: of the value)
+    float dS0, dS[NF][K + 1];          // d/d log_scale of the gate's value and of Sj[d][k], k >= 1
     float v0, vj[NF][K + 1];           // jet of v = bc + G N
-    int time_dir;                      // the direction along the time axis, or -1
 };
+
+// c = a * b for jets of derivatives (Leibniz), in place on a
+template <int K>
+PINN_HD void jet_mul(float (&a)[K + 1], const float (&b)[K + 1]) {
+    float c[K + 1];
+#pragma unroll
+    for (int n = 0; n <= K; ++n) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= n; ++k) t = fmaf(binom(n, k) * a[k], b[n - k], t);
+        c[n] = t;
+    }
+#pragma unroll
+    for (int n = 0; n <= K; ++n) a[n] = c[n];
+}
 
 template <int NF, int K>
 PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, int RS, float log_scale,
                             const float (&N)[1 + NF * K], const float* __restrict__ icj, AnsatzHi<NF, K>& st,
                             float (&u)[1 + NF * K]) {
+    // boundary factor along the line x + tau v: the product over the spatial dims of the quadratics' jets
+    // (q, q' v_i, q'' v_i^2, 0, 0) — along an axis this is (G, others q', others q'', 0, 0)
     st.G = 1.0f;
+#pragma unroll
+    for (int d = 0; d < NF; ++d) {
+        float g[K + 1];
+        g[0] = 1.0f;
+#pragma unroll
+        for (int n = 1; n <= K; ++n) g[n] = 0.0f;
+        if (P.has_bc) {
+            for (int i = 0; i < P.nsp; ++i) {
+                const float x = coords[(size_t)i * RS];
+                const float vi = P.dir_vec[d][i];
+                float q[K + 1];
+                q[0] = (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
+                q[1] = (P.lo[i] + P.hi[i] - 2.0f * x) * P.inv_w2[i] * vi;
+                q[2] = -2.0f * P.inv_w2[i] * vi * vi;
+#pragma unroll
+                for (int n = 3; n <= K; ++n) q[n] = 0.0f;
+                jet_mul<K>(g, q);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n <= K; ++n) st.Gj[d][n] = g[n];
+    }
     if (P.has_bc) {
         float G = 1.0f;
         for (int i = 0; i < P.nsp; ++i) {
@@ -261,31 +299,10 @@ PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, 
         }
         st.G = G;
     }
-    st.time_dir = -1;
 #pragma unroll
-    for (int d = 0; d < NF; ++d) {
-        const int k = P.dir_col[d];
-        st.Gj[d][0] = st.G;
-#pragma unroll
-        for (int n = 1; n <= K; ++n) st.Gj[d][n] = 0.0f;
-        if (P.has_bc && k < P.nsp) {
-            float others = 1.0f;
-            for (int i = 0; i < P.nsp; ++i) {
-                if (i != k) {
-                    const float x = coords[(size_t)i * RS];
-                    others *= (x - P.lo[i]) * (P.hi[i] - x) * P.inv_w2[i];
-                }
-            }
-            const float xk = coords[(size_t)k * RS];
-            st.Gj[d][1] = (P.lo[k] + P.hi[k] - 2.0f * xk) * P.inv_w2[k] * others;
-            st.Gj[d][2] = -2.0f * P.inv_w2[k] * others;
-        }
-        if (P.has_ic && k == P.ndims - 1) st.time_dir = d;
-    }
+    for (int d = 0; d < NF; ++d) st.Gj[d][0] = st.G;    // one value for every direction (same product, same order)
     // time gate
-    st.Sg = 1.0f;
-#pragma unroll
-    for (int n = 0; n <= K; ++n) st.dS[n] = 0.0f;
+    st.Sg = 1.0f; st.dS0 = 0.0f;
     float sg_s[K + 2];
 #pragma unroll
     for (int n = 0; n <= K + 1; ++n) sg_s[n] = 0.0f;
@@ -297,25 +314,21 @@ PINN_HD void ansatz_forward(const DevPlan& P, const float* __restrict__ coords, 
         const float sig = 1.0f / (1.0f + expf(-y));
         act_derivs<K>(PINN_ACT_SIGMOID, sig, sg_s);        // sg_s[n] = sigmoid^(n)(y), n = 1..K+1
         st.Sg = sig - 0.5f;
-        st.dS[0] = -y * sg_s[1];
+        st.dS0 = -y * sg_s[1];
     }
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
         st.Sj[d][0] = st.Sg;
-#pragma unroll
-        for (int n = 1; n <= K; ++n) st.Sj[d][n] = 0.0f;
-    }
-    if (st.time_dir >= 0) {
+        st.dS[d][0] = st.dS0;
+        // along v the gate's argument moves with speed v_t / s:  d^n/dtau^n = sigmoid^(n)(y) (v_t / s)^n, and
+        // d/d log_scale of that = -(y sigmoid^(n+1)(y) + n sigmoid^(n)(y)) (v_t / s)^n
+        const float rate = P.has_ic ? P.dir_vec[d][P.ndims - 1] * inv_s : 0.0f;
         float pw = 1.0f;
 #pragma unroll
         for (int n = 1; n <= K; ++n) {
-            pw *= inv_s;
-            const float val = sg_s[n] * pw;
-            // d/d log_scale of sigmoid^(n)(y) / s^n:  -(y sigmoid^(n+1)(y) + n sigmoid^(n)(y)) / s^n
-            st.dS[n] = -fmaf(y, sg_s[n + 1], (float)n * sg_s[n]) * pw;
-#pragma unroll
-            for (int d = 0; d < NF; ++d)
-                if (d == st.time_dir) st.Sj[d][n] = val;
+            pw *= rate;
+            st.Sj[d][n] = sg_s[n] * pw;
+            st.dS[d][n] = -fmaf(y, sg_s[n + 1], (float)n * sg_s[n]) * pw;
         }
     }
     // v = bc + G N, u = S v + ic
@@ -352,7 +365,7 @@ PINN_HD float ansatz_adjoint(const DevPlan& P, const AnsatzHi<NF, K>& st, const 
 #pragma unroll
     for (int c = 0; c < C; ++c) Nb[c] = 0.0f;
     float vb0 = P.has_ic ? st.Sg * ub[0] : ub[0];          // adjoint of the value of v
-    float sbar = P.has_ic ? st.dS[0] * st.v0 * ub[0] : 0.0f;
+    float sbar = P.has_ic ? st.dS0 * st.v0 * ub[0] : 0.0f;
 #pragma unroll
     for (int d = 0; d < NF; ++d) {
         float vb[K + 1];
@@ -366,8 +379,7 @@ PINN_HD float ansatz_adjoint(const DevPlan& P, const AnsatzHi<NF, K>& st, const 
                 for (int k = 0; k <= n; ++k) {
                     const float c = binom(n, k);
                     vb[n - k] = fmaf(c * st.Sj[d][k], un, vb[n - k]);
-                    // the gate's VALUE (k = 0) depends on log_scale along every direction, its derivatives along time
-                    if (k == 0 || d == st.time_dir) sbar = fmaf(c * st.dS[k] * st.vj[d][n - k], un, sbar);
+                    sbar = fmaf(c * st.dS[d][k] * st.vj[d][n - k], un, sbar);
                 }
             }
         } else {
@@ -514,7 +526,7 @@ PINN_HD void wgrad_input_layer(const DevPlan& P, const float* __restrict__ units
                 float e = (k < L.n_in) ? zb0 * coords[(size_t)k * RS] : 0.0f;
 #pragma unroll
                 for (int d = 0; d < NF; ++d)
-                    if (P.dir_col[d] == k) e += zb1[d];
+                    e = fmaf(zb1[d], P.dir_vec[d][k], e);
                 v[jj * PINN_MAX_DIMS + k] = e;
             }
         }

@@ -95,3 +95,4 @@ __global__ void __launch_bounds__(256, 1) hi_step_kernel(const __grid_constant__
 pinn::StepKernelFn pinn_hi_variant_nf1(int order);
 pinn::StepKernelFn pinn_hi_variant_nf2(int order);
 pinn::StepKernelFn pinn_hi_variant_nf3(int order);
+pinn::StepKernelFn pinn_hi_variant_nf4(int order);

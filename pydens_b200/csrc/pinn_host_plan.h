@@ -58,13 +58,12 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     const bool hi = s->order >= 3;
     if (hi) {
         // whole-jet plans (pinn_device_hi.cuh): what that code covers
-        if (s->nf < 1 || s->nf > 3) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d with %d derivative directions (1..3)", s->order, s->nf);
+        if (s->nf < 1 || s->nf > 4) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d with %d derivative directions (1..4)", s->order, s->nf);
         if (s->ns != 0) PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: ns must be 0 (every direction carries its whole jet)", s->order);
-        for (int d = 0; d < s->nf; ++d) {
-            if (s->dir_col[d] < 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: direction %d is not an axis", s->order, d);
+        for (int d = 0; d < s->nf; ++d)
             for (int e = 0; e < d; ++e)
-                if (s->dir_col[e] == s->dir_col[d]) PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
-        }
+                if (s->dir_col[d] >= 0 && s->dir_col[e] == s->dir_col[d])
+                    PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
         if (s->has_ic && s->ic_has_vars) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: variables inside the initial condition", s->order);
         for (int l = 0; l < Ln; ++l) {
             if (s->skip_src[l] >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: residual layouts", s->order);

@@ -220,7 +220,7 @@ extern "C" int pinn_plan_create(const PinnSpec* s, int device, PinnPlan** out) {
     if (order >= 3) {
         // derivatives of order 3 / 4: whole jets per direction (pinn_hi_kernel.cuh), one kernel per (nf, order)
         StepKernelFn f = s->nf == 1 ? pinn_hi_variant_nf1(order) : s->nf == 2 ? pinn_hi_variant_nf2(order)
-                       : s->nf == 3 ? pinn_hi_variant_nf3(order) : nullptr;
+                       : s->nf == 3 ? pinn_hi_variant_nf3(order) : s->nf == 4 ? pinn_hi_variant_nf4(order) : nullptr;
         if (!f) { delete p; return fail(PINN_E_UNSUPPORTED, "no kernel for derivative order %d with %d directions", order, s->nf); }
         const Variant v = {s->nf, 0, nullptr, nullptr, nullptr, f, nullptr, 256};
         p->var_store = v;

@@ -766,29 +766,58 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
 
 
 def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run):
-    """ Equations with derivatives of order 3 / 4 (D nested three / four times along ONE argument: u_xxx, u_xxxx):
-    every differentiated axis carries its whole Taylor jet up to the highest order met (pinn_device_hi.cuh). """
+    """ Equations with derivatives of order 3 / 4 (D nested three / four times: u_xxx, u_xxxx): every direction carries
+    its whole Taylor jet up to the highest order met (pinn_device_hi.cuh).  Directions are the differentiated
+    arguments and, for every pair (i, j) with a mixed derivative, the two diagonals p = e_i + e_j and m = e_i - e_j,
+    which carry it by polarisation (P_n, M_n = n-th derivative along p, m):
+        u_ij = (P_2 - M_2) / 4,  u_iij = (P_3 - M_3 - 2 u_jjj) / 6,  u_ijj = (P_3 + M_3 - 2 u_iii) / 6,
+        u_iijj = (P_4 + M_4 - 2 u_iiii - 2 u_jjjj) / 12      (what the biharmonic operator needs). """
     order = max(len(l.value) for l in u_leaves)
-    axes = set()
+    axes, pairs = set(), set()
     for l in u_leaves:
-        if len(set(l.value)) > 1:
-            raise NotLowerable('mixed derivatives next to derivatives of order > 2')
-        axes.update(l.value)
-    axes = sorted(axes)
-    nf = len(axes)
-    if nf > 3:
-        raise NotLowerable('derivatives of order > 2 along more than 3 arguments')
+        distinct = sorted(set(l.value))
+        axes.update(distinct)
+        if len(distinct) > 2:
+            raise NotLowerable('mixed derivatives along three arguments next to derivatives of order > 2')
+        if len(distinct) == 2:
+            counts = (l.value.count(distinct[0]), l.value.count(distinct[1]))
+            if max(counts) > 2:
+                raise NotLowerable('mixed derivative %r is not carried by the diagonals e_i +- e_j' % (l.value,))
+            pairs.add((distinct[0], distinct[1]))
+    axes, pairs = sorted(axes), sorted(pairs)
+    nf = len(axes) + 2 * len(pairs)
+    if nf > 4:
+        raise NotLowerable('derivatives of order > 2 along more than 4 directions (arguments and diagonals)')
 
-    def unit(k):
-        return [1.0 if i == k else 0.0 for i in range(total)]
+    def vec(entries):
+        return [float(entries.get(i, 0.0)) for i in range(total)]
     T.order, T.ns = order, 0
-    T.dirs, T.dir_vecs = list(axes), [unit(k) for k in axes]
+    T.dirs = list(axes) + [-1] * (2 * len(pairs))
+    T.dir_vecs = [vec({k: 1.0}) for k in axes]
+    for i, j in pairs:
+        T.dir_vecs += [vec({i: 1.0, j: 1.0}), vec({i: 1.0, j: -1.0})]
     C = 1 + nf * order
+
+    def ch(d, n):
+        return chleaf(1 + d * order + (n - 1))
     mapping = {uleaf(): chleaf(0)}
-    for d, col in enumerate(axes):
+    d_of = {col: d for d, col in enumerate(axes)}
+    for col, d in d_of.items():
         for n in range(1, order + 1):
-            mapping[uleaf((col,) * n)] = chleaf(1 + d * order + (n - 1))
+            mapping[uleaf((col,) * n)] = ch(d, n)
+    for q, (i, j) in enumerate(pairs):
+        dp, dm = len(axes) + 2 * q, len(axes) + 2 * q + 1
+        di, dj = d_of[i], d_of[j]
+        mapping[uleaf((i, j))] = mul(const(0.25), sub(ch(dp, 2), ch(dm, 2)))
+        if order >= 3:
+            mapping[uleaf((i, i, j))] = mul(const(1.0 / 6.0), sub(sub(ch(dp, 3), ch(dm, 3)), mul(const(2.0), ch(dj, 3))))
+            mapping[uleaf((i, j, j))] = mul(const(1.0 / 6.0), sub(add(ch(dp, 3), ch(dm, 3)), mul(const(2.0), ch(di, 3))))
+        if order >= 4:
+            mapping[uleaf((i, i, j, j))] = mul(const(1.0 / 12.0), sub(sub(add(ch(dp, 4), ch(dm, 4)), mul(const(2.0), ch(di, 4))),
+                                                                    mul(const(2.0), ch(dj, 4))))
     res = substitute(res, mapping)
+    if leaves(res, ('u',)):
+        raise NotLowerable('a derivative of the equation has no jet channel')
     T.residual = res
 
     ic = None
@@ -805,16 +834,22 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
     T.var_names = sorted({l.value for l in leaves(res, ('var',))})
     if len(T.var_names) > 4:
         raise NotLowerable('more than 4 trainable variables')
+    if 1 + C + len(T.var_names) > 2 + 2 * MAX_DIRS + 4:
+        raise NotLowerable('%d jet channels and %d variables exceed the outputs of a residual program' % (C, len(T.var_names)))
     var_index = {n: i for i, n in enumerate(T.var_names)}
     outputs = [res] + [diff_leaf(res, chleaf(c)) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
     T.eq_prog = lower(outputs, {}, var_index, C)
     T.n_slots = T.eq_prog.n_slots
     if ic is not None:
         jet = [ic]
-        for col in axes:
+        for dvec in T.dir_vecs:
             e = ic
             for _ in range(order):
-                e = diff_coord(e, col)
+                out = ZERO
+                for k, v in enumerate(dvec):
+                    if v != 0.0:
+                        out = add(out, mul(const(v), diff_coord(e, k)))
+                e = out
                 jet.append(e)
         T.ic_prog = lower(jet, {}, var_index, C)
         T.n_slots = max(T.n_slots, T.ic_prog.n_slots)

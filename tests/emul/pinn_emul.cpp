@@ -90,7 +90,7 @@ extern "C" int emul_step(const PinnSpec* spec, const float* params, const float*
     host_stage_weights(P, params, sw.data());
     for (int i = 0; i < P.n_params + 4; ++i) out[i] = 0.0f;
 #define CASE_HI(NF_, K_) if (spec_order(spec) == K_ && P.nf == NF_) { run_step_hi<NF_, K_>(P, sw.data(), params, points, n, inv_n, out, residual); return 0; }
-    CASE_HI(1, 3) CASE_HI(2, 3) CASE_HI(3, 3) CASE_HI(1, 4) CASE_HI(2, 4) CASE_HI(3, 4)
+    CASE_HI(1, 3) CASE_HI(2, 3) CASE_HI(3, 3) CASE_HI(4, 3) CASE_HI(1, 4) CASE_HI(2, 4) CASE_HI(3, 4) CASE_HI(4, 4)
 #undef CASE_HI
     if (spec_order(spec) >= 3) { snprintf(msg, msg_len, "no hi variant nf=%d order=%d", P.nf, spec_order(spec)); return PINN_E_UNSUPPORTED; }
 #define CASE(NF_, NS_) if (P.nf == NF_ && P.ns == NS_) { run_step<NF_, NS_>(P, sw.data(), params, points, n, inv_n, out, residual); return 0; }

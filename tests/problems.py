@@ -72,6 +72,12 @@ def _plate(f, x, y, t, D, V):                        # three directions at order
     return D(D(f, t), t) + 0.1 * (D(D(D(D(f, x), x), x), x) + D(D(D(D(f, y), y), y), y)) + D(D(D(f, x), x), x) * f
 
 
+def _biharmonic(f, x, y, D, V):                      # clamped plate: the biharmonic operator in two dimensions
+    def lap(g):
+        return D(D(g, x), x) + D(D(g, y), y)
+    return lap(lap(f)) - 8.0 * torch.sin(PI * x) * torch.sin(PI * y)
+
+
 def _ic_kdv(x):
     return torch.sin(2.0 * x) + 0.3
 
@@ -240,18 +246,20 @@ PROBLEMS = {
     'plate': dict(equation=_plate, ndims=3, nparams=0, ic=_ic_plate, bc=0, domain=(0, 1),
                   features=[8, 7, 1], activation='Tanh', layout='fafaf', ranges=[(0, 1), (0, 1), (0, .5)],
                   log_scale=0.1),
+    'biharmonic': dict(equation=_biharmonic, ndims=2, nparams=0, ic=None, bc=0.0, domain=(0, 1),
+                       features=[10, 8, 1], activation=['Tanh', Sin], layout='fafaf', ranges=[(0, 1), (0, 1)]),
 }
 
 # problems that need the five- / six-direction kernels; the GPU tests of those kernels live in their own file
 HI_DIRECTION = ('hess3d', 'heat4d', 'lap6d', 'hess3d_var')
 # problems with derivatives of order 3 / 4 (whole-jet kernels); GPU tests in the same file
-HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate')
+HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate', 'biharmonic')
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
                 'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75,
                 'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60,
                 'hess3d': 70, 'heat4d': 66, 'lap6d': 75, 'hess3d_var': 68,
-                'kdv': 72, 'beam': 69, 'ks': 65, 'ode3': 40, 'plate': 67}
+                'kdv': 72, 'beam': 69, 'ks': 65, 'ode3': 40, 'plate': 67, 'biharmonic': 71}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
@@ -259,9 +267,9 @@ GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'hea
                'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01),
                'wave3d': (12, 96, 0.001), 'heat4d': (12, 48, 0.01), 'hess3d_var': (12, 40, 0.01),
                'kdv': (15, 48, 0.005), 'plate': (10, 40, 0.005)}
-# (no trajectory for 'beam': the reference's own fp32 fit is not reproducible there — nested autograd of order 4 through
-#  sigmoids returns losses of 1.78 and 921.7 at steps where fp64 gives 0.177 and 0.169; tests/test_emul.py holds the
-#  fused math to the fp64 oracle along that fit instead)
+# (no trajectory for 'beam' and 'biharmonic': the reference's own fp32 fit is not reproducible there — nested autograd of
+#  order 4 returns losses of 1.78 and 921.7 (beam), 97.3 (biharmonic) at steps where fp64 gives 0.177, 0.169 and 5.86;
+#  tests/test_emul.py holds the fused math to the fp64 oracle along those fits instead)
 
 
 def make_points(name, batch, seed):

@@ -277,6 +277,8 @@ def test_random_high_order_problem_on_gpu_matches_fp64_oracle(seed):
     ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
     tag = '%s %s %s acts=%s n=%d' % (cfg['eq_name'], cfg['layout'], cfg['features'], acts, n)
     cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    if cfg['eq_name'] in ('biharmonic', 'mixed3'):
+        cond *= 5.0          # mixed derivatives by polarisation: (P_4 + M_4 - 2 u_xxxx - 2 u_yyyy) / 12 cancels leading digits
     assert abs(loss - ref_loss) <= 2e-5 * cond * max(abs(ref_loss), 1e-6), tag
     assert rel_l2(residual, ref_res) <= 2e-5 * cond, tag
     assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, tag

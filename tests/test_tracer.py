@@ -87,10 +87,10 @@ def test_not_lowerable_cases():
     D = T.sym_D
     with pytest.raises(T.NotLowerable):            # fifth order
         T.trace(lambda f, x: D(D(D(D(D(f, x), x), x), x), x), 1, None)
-    with pytest.raises(T.NotLowerable):            # a mixed derivative next to a third-order one
-        T.trace(lambda f, x, y: D(D(D(f, x), x), x) + D(D(f, x), y), 2, None)
-    with pytest.raises(T.NotLowerable):            # third-order mixed derivative
-        T.trace(lambda f, x, y: D(D(D(f, x), x), y), 2, None)
+    with pytest.raises(T.NotLowerable):            # u_xxxy: not carried by the diagonals e_x +- e_y
+        T.trace(lambda f, x, y: D(D(D(D(f, x), x), x), y), 2, None)
+    with pytest.raises(T.NotLowerable):            # third order next to mixed derivatives of two pairs: 3 + 4 directions
+        T.trace(lambda f, x, y, z: D(D(D(f, x), x), x) + D(D(f, x), y) + D(D(f, y), z), 3, None)
     with pytest.raises(T.NotLowerable):            # more than 6 directions (3 axes + 3 diagonals + t)
         T.trace(lambda f, x, y, z, t: D(D(f, x), y) + D(D(f, y), z) + D(D(f, x), z) + D(f, t), 4, None)
     with pytest.raises(T.NotLowerable):            # data-dependent branch
@@ -145,6 +145,29 @@ def test_third_and_fourth_order_derivatives_carry_whole_jets():
     with pytest.raises(T.NotLowerable):            # variables inside the initial condition stay on the order-2 path
         T.trace(lambda u, x, t: D(D(D(u, x), x), x) + D(u, t), 2, None,
                 initial_condition=lambda x: x * T.Sym(T.var('amp')), ndims_spatial=1)
+
+
+def test_mixed_derivatives_next_to_high_orders_ride_on_two_diagonals():
+    """ The biharmonic operator: u_xxxx + 2 u_xxyy + u_yyyy.  Directions x, y, x+y, x-y, each with its jet up to order 4;
+    u_xxyy = (P_4 + M_4 - 2 u_xxxx - 2 u_yyyy) / 12. """
+    D = T.sym_D
+    D2 = lambda u, x: D(D(u, x), x)
+    tr = T.trace(lambda u, x, y: D2(D2(u, x), x) + 2.0 * D2(D2(u, x), y) + D2(D2(u, y), y), 2, None)
+    assert (tr.order, tr.nf, tr.dirs, tr.channels) == (4, 4, [0, 1, -1, -1], 17)
+    assert tr.dir_vecs[2] == [1.0, 1.0] and tr.dir_vecs[3] == [1.0, -1.0]
+    rng = np.random.RandomState(2)
+    jet = rng.normal(size=(17, 4))
+    outs = T.run_program(tr.eq_prog, jet, rng.uniform(size=(2, 4)), [])
+    x4, y4, p4, m4 = jet[4], jet[8], jet[12], jet[16]
+    np.testing.assert_allclose(outs[0], x4 + y4 + 2.0 * (p4 + m4 - 2.0 * x4 - 2.0 * y4) / 12.0, rtol=1e-12)
+    np.testing.assert_allclose(outs[1 + 4], np.full(4, 1.0 - 4.0 / 12.0), rtol=1e-12)
+    np.testing.assert_allclose(outs[1 + 12], np.full(4, 2.0 / 12.0), rtol=1e-12)
+    # third order: u_xxy = (P_3 - M_3 - 2 u_yyy) / 6
+    tr = T.trace(lambda u, x, y: D(D2(u, x), y), 2, None)
+    assert (tr.order, tr.nf, tr.channels) == (3, 4, 13)
+    jet = rng.normal(size=(13, 3))
+    outs = T.run_program(tr.eq_prog, jet, rng.uniform(size=(2, 3)), [])
+    np.testing.assert_allclose(outs[0], (jet[9] - jet[12] - 2.0 * jet[6]) / 6.0, rtol=1e-12)
 
 
 def test_variables_inside_initial_condition():
