@@ -26,15 +26,21 @@ BINARY = [
 ]
 
 
-def random_equation(rng, total):
-    """ -> (callable eq(u, *xs, D, V), description).  Leaves are created lazily so D() is called inside the trace. """
+def random_equation(rng, total, high=False):
+    """ -> (callable eq(u, *xs, D, V), description).  Leaves are created lazily so D() is called inside the trace.
+    `high`: also derivatives of order 3 / 4 (and mixed ones carried by the diagonals) among the leaves. """
     second = rng.rand() < 0.6
     mixed = total >= 2 and rng.rand() < 0.3
     use_var = rng.rand() < 0.4
+    extra = []
+    if high:
+        extra = ['uxxx'] + (['uxxxx'] if rng.rand() < 0.6 else []) + (['uyyy'] if total >= 2 and rng.rand() < 0.4 else [])
+        if total >= 2 and rng.rand() < 0.4:
+            extra += ['uxxy'] + (['uxxyy'] if 'uxxxx' in extra else [])
 
     def leaf():
         kinds = ['u', 'u', 'ux', 'x', 'const'] + (['uxx'] if second else []) + (['uxy'] if mixed else []) \
-            + (['y', 'uy'] if total >= 2 else []) + (['var'] if use_var else [])
+            + (['y', 'uy'] if total >= 2 else []) + (['var'] if use_var else []) + extra
         k = kinds[int(rng.randint(len(kinds)))]
         c = float(np.round(rng.uniform(-2, 2), 2))
         return (k, c)
@@ -48,6 +54,8 @@ def random_equation(rng, total):
 
     # make sure the residual depends on u and on a derivative
     root = ('bin', 0, ('bin', 0, tree(int(rng.randint(2, 5))), ('leaf', ('ux', 0.0))), ('leaf', ('u', 0.0)))
+    if high:                                               # ... and on a derivative of order 3 at least
+        root = ('bin', 0, root, ('leaf', (extra[int(rng.randint(len(extra)))], 0.0)))
 
     def describe(t):
         if t[0] == 'leaf':
@@ -66,6 +74,9 @@ def random_equation(rng, total):
             if kind not in cache:
                 cache[kind] = {'u': lambda: u, 'x': lambda: x, 'y': lambda: y, 'ux': lambda: D(u, x),
                                'uy': lambda: D(u, y), 'uxx': lambda: D(D(u, x), x), 'uxy': lambda: D(D(u, x), y),
+                               'uxxx': lambda: D(D(D(u, x), x), x), 'uxxxx': lambda: D(D(D(D(u, x), x), x), x),
+                               'uyyy': lambda: D(D(D(u, y), y), y), 'uxxy': lambda: D(D(D(u, x), x), y),
+                               'uxxyy': lambda: D(D(D(D(u, x), x), y), y),
                                'var': lambda: V('k', 0.7)}[kind]()
             return cache[kind]
 
@@ -105,6 +116,41 @@ def test_random_expression_matches_autograd(seed):
     prob.load_flat(torch.from_numpy(params.astype(np.float64)))
     ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
     cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
+    assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text
+
+
+@pytest.mark.parametrize('seed', list(range(100)))
+def test_random_high_order_expression_matches_autograd(seed):
+    """ The same with derivatives of order 3 / 4 among the leaves: the whole-jet path (tracer polarisation included). """
+    rng = np.random.RandomState(7000 + seed)
+    total = int(rng.randint(1, 3))
+    eq, text, use_var = random_equation(rng, total, high=True)
+    features, acts = [6, 5, 1], ['Tanh', 'Sigmoid']
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    try:
+        traced = T.trace(lambda u, *xs: eq(u, *xs, D=T.sym_D, V=sym_V), total, None)
+    except T.NotLowerable as exc:
+        assert any(w in str(exc) for w in ('slots', 'instructions', 'directions', 'outputs', 'diagonals')), (text, exc)
+        return
+    assert traced.order in (3, 4), text
+    spec = N.build_spec([total] + features, ['tanh', 'sigmoid', 'none'], total, 0, False, 0.0, False,
+                        [(0.0, 1.0)] * total, traced)
+    uses_var = 'k' in traced.var_names
+    if 'var' in text and not uses_var:
+        return
+    prob = ap.Problem(eq, ndims=total, features=features, activation=acts, dtype=torch.float64,
+                      variables={'k': 0.7} if uses_var else None, seed=seed, layout='fafaf')
+    params = prob.flat_params().numpy().astype(np.float32)
+    assert spec.n_params == params.size, text
+    pts = rng.uniform(0.05, 0.95, size=(40, total)).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params, pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    if 'uxxy' in text:
+        cond *= 5.0                                        # polarisation cancels leading digits
     assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
     assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
     assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text
