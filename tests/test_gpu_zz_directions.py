@@ -286,36 +286,35 @@ def test_random_high_order_problem_on_gpu_matches_fp64_oracle(seed):
     assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag
 
 
-def test_kdv_through_the_public_api_follows_the_autograd_path():
-    """ The user-level call with D nested three times: the fused fit (host batches, then in-kernel sampling with graph
-    replay and Adam in the kernel's tail) against the device-aware restatement of the reference loop (backend='torch':
-    nested autograd.grad) on identical initial weights and identical batches. """
+def test_kdv_through_the_public_api_follows_the_fp64_oracle():
+    """ The user-level call with D nested three times: the fused fit (host batches; then in-kernel sampling with graph
+    replay and Adam in the kernel's tail) against the oracle port of the reference loop in fp64 on identical initial
+    weights and batches.  (fp64 because fp32 nested autograd of order 3 is a noisy yardstick: on the CPU its loss is off by
+    1 % at single steps of this very fit, while this path's host build follows fp64 to 1.5e-6.) """
     from pydens_b200 import Solver, D
 
     def kdv(f, x, t):
         return D(f, t) + 6.0 * f * D(f, x) + D(D(D(f, x), x), x)
-
-    def make(backend):
-        torch.manual_seed(0)
-        return Solver(kdv, ndims=2, initial_condition=lambda x: torch.sin(np.pi * x), boundary_condition=0.0,
-                      layout='fafaf', features=[16, 16, 1], activation='Tanh', backend=backend)
+    torch.manual_seed(0)
+    fused = Solver(kdv, ndims=2, initial_condition=lambda x: torch.sin(np.pi * x), boundary_condition=0.0,
+                   layout='fafaf', features=[16, 16, 1], activation='Tanh', backend='fused')
+    start = fused.flat_params().cpu().numpy()
     rng = np.random.RandomState(3)
     batches = [rng.uniform(size=(256, 2)).astype(np.float32) for _ in range(25)]
-    fused, ref = make('fused'), make('torch')
+    prob = ap.Problem(lambda u, x, t, D, V: D(u, t) + 6.0 * u * D(u, x) + D(D(D(u, x), x), x), ndims=2,
+                      initial_condition=lambda x: torch.sin(np.pi * x), boundary_condition=0.0, domain=(0, 1),
+                      features=[16, 16, 1], activation='Tanh', dtype=torch.float64)
+    prob.load_flat(torch.from_numpy(start.astype(np.float64)))
+    ref = ap.fit(prob, 25, 256, lr=0.005, point_stream=lambda i: torch.from_numpy(batches[i].astype(np.float64)))
     fused.fit(niters=25, batch_size=256, sampler=Replay(batches), lr=0.005)
-    ref.fit(niters=25, batch_size=256, sampler=Replay(batches), lr=0.005)
     assert fused._engine is not None and fused._engine.spec.order == 3
-    a, b = np.asarray(fused.losses, dtype=np.float64), np.asarray(ref.losses, dtype=np.float64)
-    assert a.shape == b.shape == (25,)
-    # the yardstick itself is fp32 nested autograd of order 3: its loss carries up to ~1 % of rounding noise at single
-    # steps (measured on the CPU against this path's host build: 9e-3, with parameters agreeing to 1e-6) — the curve is
-    # compared at that width, the trained weights and the solution tightly
-    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 5e-2
-    assert np.median(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 2e-3
-    wf = torch.cat([p.detach().reshape(-1) for l in fused.model.conv_block.linears for p in (l.weight, l.bias)])
-    wr = torch.cat([p.detach().reshape(-1) for l in ref.model.conv_block.linears for p in (l.weight, l.bias)])
-    assert float((wf - wr).norm() / wr.norm()) <= 1e-3
+    a = np.asarray(fused.losses, dtype=np.float64)
+    assert a.shape == ref.shape == (25,)
+    assert np.max(np.abs(a - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-3
+    final, want = fused.flat_params().cpu().numpy(), prob.flat_params().numpy()
+    assert np.linalg.norm(final - want) / np.linalg.norm(want) <= 1e-3
     xs = np.linspace(0, 1, 7)
-    assert np.abs(fused.predict(xs, 0.3) - ref.predict(xs, 0.3)).max() <= 1e-3
+    pts = np.stack([xs, np.full(7, 0.3)], axis=1)
+    assert np.abs(fused.predict(xs, 0.3).reshape(-1) - prob.predict(pts)).max() <= 1e-4
     fused.fit(niters=64, batch_size=4000, lr=0.005)                  # in-kernel sampling, graph replay
     assert len(fused.losses) == 89 and np.isfinite(np.asarray(fused.losses, dtype=np.float64)).all()
