@@ -581,6 +581,17 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw, const f
     for (int i = 0; i < PINN_MAX_VARS; ++i)
         if (i < P.n_vars) part.vbar[i] = fmaf(rb, scr[(size_t)P.eq_out[1 + C + i] * RS], part.vbar[i]);
 
+    if (P.ic_has_vars) {                       // u_c = S v_c + ic_c: variables of the initial condition (README.md:112-118)
+#pragma unroll
+        for (int i = 0; i < PINN_MAX_VARS; ++i) {
+            if (i < P.n_vars) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    part.vbar[i] = fmaf(ub[c], scr[(size_t)P.ic_out[C * (1 + i) + c] * RS], part.vbar[i]);
+            }
+        }
+    }
+
     float Nb[C];
     part.sbar += ansatz_adjoint<NF, K>(P, as, ub, Nb);
 

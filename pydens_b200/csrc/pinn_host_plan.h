@@ -64,7 +64,6 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
             for (int e = 0; e < d; ++e)
                 if (s->dir_col[d] >= 0 && s->dir_col[e] == s->dir_col[d])
                     PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
-        if (s->has_ic && s->ic_has_vars) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: variables inside the initial condition", s->order);
         for (int l = 0; l < Ln; ++l) {
             if (s->skip_src[l] >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: residual layouts", s->order);
             if (s->act[l] != PINN_ACT_NONE && s->act[l] != PINN_ACT_TANH && s->act[l] != PINN_ACT_SIGMOID && s->act[l] != PINN_ACT_SIN)
@@ -74,6 +73,8 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
     const int C = spec_channels(s);
     if (1 + C + s->n_vars > (int)(sizeof(s->eq_out) / sizeof(s->eq_out[0])))
         PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "%d jet channels + %d variables exceed the program's outputs", C, s->n_vars);
+    if (s->has_ic && C * (1 + (s->ic_has_vars ? s->n_vars : 0)) > (int)(sizeof(s->ic_out) / sizeof(s->ic_out[0])))
+        PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "%d jet channels x (1 + %d variables) exceed the initial condition's outputs", C, s->n_vars);
     for (int d = 0; d < s->nf; ++d) {
         if (s->dir_col[d] >= total) PINN_PLAN_FAIL(PINN_E_INVALID, "dir_col[%d]", d);
         bool any = false;

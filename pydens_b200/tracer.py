@@ -829,12 +829,11 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
             ic = const(float(np.float32(initial_condition)))
         if leaves(ic, ('u',)):
             raise NotLowerable('initial_condition must not depend on the solution')
-        if leaves(ic, ('var',)):
-            raise NotLowerable('variables inside the initial condition next to derivatives of order > 2')
-    T.var_names = sorted({l.value for l in leaves(res, ('var',))})
+    ic_vars = {l.value for l in leaves(ic, ('var',))} if ic is not None else set()
+    T.var_names = sorted({l.value for l in leaves(res, ('var',))} | ic_vars)
     if len(T.var_names) > 4:
         raise NotLowerable('more than 4 trainable variables')
-    if 1 + C + len(T.var_names) > 2 + 2 * MAX_DIRS + 4:
+    if 1 + C + len(T.var_names) > 2 + 2 * MAX_DIRS + 4 or (ic_vars and C * (1 + len(T.var_names)) > (1 + 2 * MAX_DIRS) * 5):
         raise NotLowerable('%d jet channels and %d variables exceed the outputs of a residual program' % (C, len(T.var_names)))
     var_index = {n: i for i, n in enumerate(T.var_names)}
     outputs = [res] + [diff_leaf(res, chleaf(c)) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
@@ -851,7 +850,12 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
                         out = add(out, mul(const(v), diff_coord(e, k)))
                 e = out
                 jet.append(e)
-        T.ic_prog = lower(jet, {}, var_index, C)
+        T.ic_has_vars = bool(ic_vars)
+        base = C
+        if T.ic_has_vars:               # partials w.r.t. every variable; slots above the equation's (they outlive it)
+            jet = jet + [diff_leaf(j, var(n)) for n in T.var_names for j in jet]
+            base = T.eq_prog.n_slots
+        T.ic_prog = lower(jet, {}, var_index, base)
         T.n_slots = max(T.n_slots, T.ic_prog.n_slots)
     return T
 

@@ -78,6 +78,14 @@ def _biharmonic(f, x, y, D, V):                      # clamped plate: the biharm
     return lap(lap(f)) - 8.0 * torch.sin(PI * x) * torch.sin(PI * y)
 
 
+def _kdv_icvar(f, x, t, D, V):                       # order 3 with variables in the equation AND in the initial condition
+    return D(f, t) + V('speed', 1.5) * f * D(f, x) + 0.2 * D(D(D(f, x), x), x)
+
+
+def _icf_kdv(V):
+    return lambda x: V('amp', 0.7) * torch.sin(2.0 * x) + V('shift', 0.2) ** 2 * x
+
+
 def _ic_kdv(x):
     return torch.sin(2.0 * x) + 0.3
 
@@ -246,6 +254,9 @@ PROBLEMS = {
     'plate': dict(equation=_plate, ndims=3, nparams=0, ic=_ic_plate, bc=0, domain=(0, 1),
                   features=[8, 7, 1], activation='Tanh', layout='fafaf', ranges=[(0, 1), (0, 1), (0, .5)],
                   log_scale=0.1),
+    'kdv_icvar': dict(equation=_kdv_icvar, ndims=2, nparams=0, ic=None, ic_factory=_icf_kdv, bc=0.0, domain=[(0, 2), (0, 1)],
+                      features=[9, 7, 1], activation='Tanh', layout='fafaf',
+                      variables={'amp': 0.7, 'shift': 0.2, 'speed': 1.5}, ranges=[(0, 2), (0, 1)], log_scale=0.1),
     'biharmonic': dict(equation=_biharmonic, ndims=2, nparams=0, ic=None, bc=0.0, domain=(0, 1),
                        features=[10, 8, 1], activation=['Tanh', Sin], layout='fafaf', ranges=[(0, 1), (0, 1)]),
 }
@@ -253,20 +264,20 @@ PROBLEMS = {
 # problems that need the five- / six-direction kernels; the GPU tests of those kernels live in their own file
 HI_DIRECTION = ('hess3d', 'heat4d', 'lap6d', 'hess3d_var')
 # problems with derivatives of order 3 / 4 (whole-jet kernels); GPU tests in the same file
-HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate', 'biharmonic')
+HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate', 'biharmonic', 'kdv_icvar')
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
                 'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75,
                 'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60,
                 'hess3d': 70, 'heat4d': 66, 'lap6d': 75, 'hess3d_var': 68,
-                'kdv': 72, 'beam': 69, 'ks': 65, 'ode3': 40, 'plate': 67, 'biharmonic': 71}
+                'kdv': 72, 'beam': 69, 'ks': 65, 'ode3': 40, 'plate': 67, 'biharmonic': 71, 'kdv_icvar': 74}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
                'burgers': (20, 64, 0.01), 'ode_var': (20, 50, 0.05), 'heat1d_icvar': (20, 48, 0.02), 'heat_resnet': (15, 40, 0.01), 'mixed_ic': (15, 40, 0.01),
                'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01),
                'wave3d': (12, 96, 0.001), 'heat4d': (12, 48, 0.01), 'hess3d_var': (12, 40, 0.01),
-               'kdv': (15, 48, 0.005), 'plate': (10, 40, 0.005)}
+               'kdv': (15, 48, 0.005), 'plate': (10, 40, 0.005), 'kdv_icvar': (15, 48, 0.01)}
 # (no trajectory for 'beam' and 'biharmonic': the reference's own fp32 fit is not reproducible there — nested autograd of
 #  order 4 returns losses of 1.78 and 921.7 (beam), 97.3 (biharmonic) at steps where fp64 gives 0.177, 0.169 and 5.86;
 #  tests/test_emul.py holds the fused math to the fp64 oracle along those fits instead)

@@ -142,9 +142,12 @@ def test_third_and_fourth_order_derivatives_carry_whole_jets():
     assert np.all(ic[4] == 0.0) and np.all(ic[6] == 0.0)            # the initial condition does not depend on t
     tr = T.trace(lambda u, x, t: D(D(u, t), t) + D(D(D(D(u, x), x), x), x) * T.Sym(T.var('q')), 2, None)
     assert (tr.order, tr.channels, tr.var_names) == (4, 9, ['q'])
-    with pytest.raises(T.NotLowerable):            # variables inside the initial condition stay on the order-2 path
-        T.trace(lambda u, x, t: D(D(D(u, x), x), x) + D(u, t), 2, None,
-                initial_condition=lambda x: x * T.Sym(T.var('amp')), ndims_spatial=1)
+    tr = T.trace(lambda u, x, t: D(D(D(u, x), x), x) + D(u, t), 2, None,              # a variable inside the initial condition
+                 initial_condition=lambda x: torch.sin(x) * T.Sym(T.var('amp')), ndims_spatial=1)
+    assert tr.ic_has_vars and tr.var_names == ['amp'] and len(tr.ic_prog.outs) == 2 * 7
+    ic = T.run_program(tr.ic_prog, np.zeros((7, 5)), coords, [1.5])
+    np.testing.assert_allclose(ic[3], -1.5 * np.cos(x), rtol=1e-12)                    # d3/dx3 of amp sin x
+    np.testing.assert_allclose(ic[7 + 1], np.cos(x), rtol=1e-12)                       # d/d amp of d/dx
 
 
 def test_mixed_derivatives_next_to_high_orders_ride_on_two_diagonals():
