@@ -12,11 +12,13 @@
 // transposed product, including d/d log_scale through the time gate.
 //
 // Written per THREAD like pinn_device.cuh and `__host__ __device__` for the same reason: tests/emul compiles these
-// very functions with g++ and checks them against the fp64 oracle.  Scope: plain dense chains, tanh / sigmoid / sin
-// (and the linear last layer), axis-aligned directions, no variables inside the initial condition — everything else about
-// a problem (samplers, variables in the equation, domains, boundary / initial conditions) is as in the main path.
-// This path favours clarity over the last FMA: it exists so that such equations stay on the GPU in one launch
-// instead of falling back to nested autograd graphs.
+// very functions with g++ and checks them against the fp64 oracle.  Scope: plain dense chains (no residual layouts)
+// with any of the fused activations; directions are the differentiated arguments plus, per pair of arguments with a
+// mixed derivative, the two diagonals e_i +- e_j that carry it by polarisation (u_xxyy = ((d_x+d_y)^4 + (d_x-d_y)^4
+// - 2 u_xxxx - 2 u_yyyy) / 12: what the biharmonic operator needs); samplers, variables (in the equation and in the
+// initial condition), domains, boundary / initial conditions are as in the main path.  This path favours clarity over
+// the last FMA: it exists so that such equations stay on the GPU in one launch instead of falling back to nested
+// autograd graphs.
 #pragma once
 
 #include "pinn_device.cuh"
@@ -56,6 +58,29 @@ PINN_HD void act_derivs(int act, float a, float (&s)[K + 2]) {
 #endif
         s[1] = cs; s[2] = -sn; s[3] = -cs; s[4] = sn;
         if (K + 1 >= 5) s[K + 1 >= 5 ? 5 : 0] = cs;
+    } else if (act == PINN_ACT_SOFTPLUS || act == PINN_ACT_SILU) {     // z-stored; both are built from the logistic function
+        const float z = a;
+        const float sg = fmaf(0.5f, tanh_acc(0.5f * z), 0.5f);
+        float g[K + 2];                                   // g[n] = n-th derivative of the logistic function at z
+        act_derivs<K>(PINN_ACT_SIGMOID, sg, g);
+        if (act == PINN_ACT_SOFTPLUS) {                   // softplus' = logistic
+            s[1] = sg;
+#pragma unroll
+            for (int k = 2; k <= K + 1; ++k) s[k] = g[k - 1];
+        } else {                                          // SiLU = z logistic(z): s_k = k g_{k-1} + z g_k
+            s[1] = fmaf(z, g[1], sg);
+#pragma unroll
+            for (int k = 2; k <= K + 1; ++k) s[k] = fmaf(z, g[k], (float)k * g[k - 1]);
+        }
+    } else if (act == PINN_ACT_GELU) {                    // z Phi(z): s_k = k phi^(k-2) + z phi^(k-1), phi^(n) = He_n(-z)... spelled out
+        const float z = a, z2 = z * z;
+        const float phi = 0.3989422804014327f * expf(-0.5f * z2);
+        const float Phi = 0.5f * erfcf(-0.7071067811865476f * z);
+        s[1] = fmaf(z, phi, Phi);
+        s[2] = phi * (2.0f - z2);
+        s[3] = phi * z * (z2 - 4.0f);
+        s[4] = phi * fmaf(fmaf(-1.0f, z2, 7.0f), z2, -4.0f);
+        if (K + 1 >= 5) s[K + 1 >= 5 ? 5 : 0] = phi * z * fmaf(fmaf(1.0f, z2, -11.0f), z2, 18.0f);
     } else {
         s[1] = 1.0f;
 #pragma unroll
@@ -63,8 +88,14 @@ PINN_HD void act_derivs(int act, float a, float (&s)[K + 2]) {
     }
 }
 
-// value of a hidden unit from what its row stores (tanh / sigmoid / identity store the value, sin stores z)
-PINN_HD float act_value(int act, float stored) { return act == PINN_ACT_SIN ? sinf(stored) : stored; }
+// value of a hidden unit from what its row stores (tanh / sigmoid / identity store the value, the others store z)
+PINN_HD float act_value(int act, float stored) {
+    if (act == PINN_ACT_SIN) return sinf(stored);
+    if (act == PINN_ACT_SOFTPLUS) return fmaxf(stored, 0.0f) + log1pf(expf(-fabsf(stored)));
+    if (act == PINN_ACT_SILU) return stored * fmaf(0.5f, tanh_acc(0.5f * stored), 0.5f);
+    if (act == PINN_ACT_GELU) return stored * 0.5f * erfcf(-0.7071067811865476f * stored);
+    return stored;
+}
 
 // Post-activation jet of one direction from its pre-activation jet z[1..K] (index 0 unused).
 template <int K>

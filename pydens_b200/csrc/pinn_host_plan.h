@@ -66,8 +66,7 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
                     PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
         for (int l = 0; l < Ln; ++l) {
             if (s->skip_src[l] >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: residual layouts", s->order);
-            if (s->act[l] != PINN_ACT_NONE && s->act[l] != PINN_ACT_TANH && s->act[l] != PINN_ACT_SIGMOID && s->act[l] != PINN_ACT_SIN)
-                PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: activation %d (tanh / sigmoid / sin only)", s->order, s->act[l]);
+
         }
     }
     const int C = spec_channels(s);

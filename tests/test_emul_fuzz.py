@@ -254,7 +254,7 @@ def _random_high_order_problem(seed):
     total = ndims + nparams
     depth = int(rng.randint(1, 4))                               # hidden layers (the oracle's nested autograd needs one)
     widths = [int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 23])) for _ in range(depth)]
-    acts = [['Tanh', 'Sigmoid', P.Sin][int(rng.randint(3))] for _ in range(depth)]
+    acts = [ACTS[int(rng.randint(len(ACTS)))] for _ in range(depth)]
     eqs = _high_order_equations(ndims)
     name, eq = eqs[int(rng.randint(len(eqs)))]
     has_ic = ndims >= 2 and bool(rng.rand() < 0.6)
