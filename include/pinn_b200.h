@@ -192,7 +192,7 @@ typedef struct PinnSpec {
                                    equations): EVERY direction carries its Taylor jet up to this order — channel
                                    1 + d*order + (k-1) holds the k-th derivative along direction d, channels = 1 + nf*order;
                                    ns is ignored (0); nf <= 4 (axes, and diagonals e_i +- e_j that carry mixed derivatives by
-                                   polarisation), plain dense chains (no residual layouts) */
+                                   polarisation) */
 } PinnSpec;
 
 typedef struct PinnPlan PinnPlan;

@@ -12,7 +12,7 @@
 // transposed product, including d/d log_scale through the time gate.
 //
 // Written per THREAD like pinn_device.cuh and `__host__ __device__` for the same reason: tests/emul compiles these
-// very functions with g++ and checks them against the fp64 oracle.  Scope: plain dense chains (no residual layouts)
+// very functions with g++ and checks them against the fp64 oracle.  Scope: dense chains and residual layouts ('R ... +')
 // with any of the fused activations; directions are the differentiated arguments plus, per pair of arguments with a
 // mixed derivative, the two diagonals e_i +- e_j that carry it by polarisation (u_xxyy = ((d_x+d_y)^4 + (d_x-d_y)^4
 // - 2 u_xxxx - 2 u_yyyy) / 12: what the biharmonic operator needs); samplers, variables (in the equation and in the
@@ -176,8 +176,8 @@ PINN_HD void fwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, co
     const float* bias = sw + L.b_s;
     const ActC out_act = make_actc(L.act);
     float* out_rows = units + (size_t)L.unit_base * C * RS;
-    const float* in_rows = l > 0 ? units + (size_t)P.layer[l - 1].unit_base * C * RS : nullptr;
-    const int in_act = l > 0 ? P.layer[l - 1].act : PINN_ACT_NONE;
+    int in_act = PINN_ACT_NONE;                          // a residual layer below is read from its post buffer, as identity
+    const float* in_rows = l > 0 ? layer_output<true>(P, l - 1, units, C, RS, in_act) : nullptr;
 #pragma unroll 1
     for (int j0 = 0; j0 < L.n_out; j0 += 4) {
         float acc[4][C];
@@ -227,6 +227,26 @@ PINN_HD void fwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, co
     }
 }
 
+// Residual layer l ('... R ... fa+', reference Block layout letters): post buffer <- act-jet(stored jet of l) + output of
+// layer skip_src (whole jets add channel by channel); consumers read the buffer like the output of an identity activation.
+template <int NF, int K>
+PINN_HD void skip_sum_jets(const DevPlan& P, int l, float* __restrict__ units, int RS) {
+    constexpr int C = 1 + NF * K;
+    const DevLayer& L = P.layer[l];
+    int src_act;
+    const float* src_rows = layer_output<true>(P, L.skip_src, units, C, RS, src_act);
+    const float* pre_rows = units + (size_t)L.unit_base * C * RS;
+    float* post_rows = units + (size_t)L.post_base * C * RS;
+#pragma unroll 1
+    for (int j = 0; j < L.n_out; ++j) {
+        float a[C], b[C];
+        load_post<NF, K>(pre_rows + (size_t)j * C * RS, RS, L.act, a);
+        load_post<NF, K>(src_rows + (size_t)j * C * RS, RS, src_act, b);
+#pragma unroll
+        for (int c = 0; c < C; ++c) post_rows[((size_t)j * C + c) * RS] = a[c] + b[c];
+    }
+}
+
 // Last layer (one output unit, no activation): the network jet N lands in registers.
 template <int NF, int K>
 PINN_HD void fwd_final(const DevPlan& P, const float* __restrict__ sw, const float* __restrict__ coords,
@@ -246,8 +266,8 @@ PINN_HD void fwd_final(const DevPlan& P, const float* __restrict__ sw, const flo
                 N[chan(K, d, 1)] = fmaf(w[k], P.dir_vec[d][k], N[chan(K, d, 1)]);
         }
     } else {
-        const float* in_rows = units + (size_t)P.layer[Ln - 2].unit_base * C * RS;
-        const int in_act = P.layer[Ln - 2].act;
+        int in_act;
+        const float* in_rows = layer_output<true>(P, Ln - 2, units, C, RS, in_act);
 #pragma unroll 1
         for (int m = 0; m < L.n_in; ++m) {
             float p[C];
@@ -440,6 +460,10 @@ PINN_HD float ansatz_adjoint(const DevPlan& P, const AnsatzHi<NF, K>& st, const 
 // (reduced over the warp, 4 output units x 4 input units per batch) and, fused, the adjoints of the layer below —
 // pushed through that layer's activation and written over its stored jet in place.  Rows / columns past the end are
 // read from clamped addresses and meet zero-padded weights; their gradient entries are dropped at the sink.
+// Residual wiring around the layer below (the bookkeeping of pinn::bwd_layer<..., SKIP = true>): when B closes a
+// residual block its output was read from its post buffer, and the adjoint of that output also belongs to the block's
+// skip source — it is stashed in the (now dead) post buffer; when B is the source of a skip, the adjoint stashed by the
+// closing layer `B.adj_from` is added before B's activation.
 template <int NF, int K>
 PINN_HD void bwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, float* __restrict__ units, int RS,
                        const GradSink& sink, float* __restrict__ dump_rows) {
@@ -449,13 +473,17 @@ PINN_HD void bwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, fl
     const float* W = sw + L.w_s;                          // [n_out_p4][n_in_p8], zero padded
     const float* out_rows = units + (size_t)L.unit_base * C * RS;
     float* in_rows = units + (size_t)B.unit_base * C * RS;
+    int load_act;
+    const float* load_rows = layer_output<true>(P, l - 1, units, C, RS, load_act);
+    const float* adj_in = B.adj_from >= 0 ? units + (size_t)P.layer[B.adj_from].post_base * C * RS : nullptr;
+    float* adj_out = B.skip_src >= 0 ? units + (size_t)B.post_base * C * RS : nullptr;
 #pragma unroll 1
     for (int m0 = 0; m0 < L.n_in; m0 += 4) {
         float post[4][C], acc[4][C];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             const int m = m0 + h < L.n_in ? m0 + h : L.n_in - 1;
-            load_post<NF, K>(in_rows + (size_t)m * C * RS, RS, B.act, post[h]);
+            load_post<NF, K>(load_rows + (size_t)m * C * RS, RS, load_act, post[h]);
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[h][c] = 0.0f;
         }
@@ -493,6 +521,19 @@ PINN_HD void bwd_layer(const DevPlan& P, int l, const float* __restrict__ sw, fl
         for (int h = 0; h < 4; ++h) {
             const bool ok = m0 + h < L.n_in;
             float* row = in_rows + (size_t)(ok ? m0 + h : 0) * C * RS;
+            if (adj_in) {
+                const float* ai = adj_in + (size_t)(ok ? m0 + h : 0) * C * RS;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[h][c] += ai[(size_t)c * RS];
+            }
+            if (adj_out) {
+                float* ao = adj_out + (size_t)(ok ? m0 + h : 0) * C * RS;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float* dst = ok ? ao + (size_t)c * RS : dump_rows;
+                    *dst = acc[h][c];
+                }
+            }
             float s[K + 2];
             act_derivs<K>(B.act, row[0], s);
             float zb0 = s[1] * acc[h][0];
@@ -583,7 +624,10 @@ PINN_HD float point_step(const DevPlan& P, const float* __restrict__ sw, const f
     float* scr = st + (size_t)P.row_scr * RS;
 
 #pragma unroll 1
-    for (int l = 0; l + 1 < Ln; ++l) fwd_layer<NF, K>(P, l, sw, coords, units, RS);
+    for (int l = 0; l + 1 < Ln; ++l) {
+        fwd_layer<NF, K>(P, l, sw, coords, units, RS);
+        if (P.layer[l].skip_src >= 0) skip_sum_jets<NF, K>(P, l, units, RS);
+    }
     float N[C];
     fwd_final<NF, K>(P, sw, coords, units, RS, N);
 

@@ -64,10 +64,6 @@ inline int build_dev_plan(const PinnSpec* s, DevPlan& h, int& fwd_rows, int& fwd
             for (int e = 0; e < d; ++e)
                 if (s->dir_col[d] >= 0 && s->dir_col[e] == s->dir_col[d])
                     PINN_PLAN_FAIL(PINN_E_INVALID, "order %d: directions %d and %d coincide", s->order, e, d);
-        for (int l = 0; l < Ln; ++l) {
-            if (s->skip_src[l] >= 0) PINN_PLAN_FAIL(PINN_E_UNSUPPORTED, "order %d: residual layouts", s->order);
-
-        }
     }
     const int C = spec_channels(s);
     if (1 + C + s->n_vars > (int)(sizeof(s->eq_out) / sizeof(s->eq_out[0])))

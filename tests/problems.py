@@ -266,19 +266,26 @@ PROBLEMS = {
     'ks_gelu': dict(equation=_ks, ndims=2, nparams=0, ic=0.4, bc=None, domain=[(0, 3), (0, 1)],
                     features=[10, 8, 6, 1], activation=['GELU', 'SiLU', 'Softplus'], layout='fafafaf',
                     ranges=[(0, 3), (0, 1)]),
+    # residual layouts under derivatives of order 3 / 4: a two-layer block, and two chained one-layer blocks
+    'kdv_resnet': dict(equation=_kdv, ndims=2, nparams=0, ic=_ic_kdv, bc=0.1, domain=[(-1, 2), (0, 1.5)],
+                       features=[8, 8, 8, 1], activation=['Tanh', 'SiLU', 'Sigmoid'], layout='fa R fa fa+ f',
+                       ranges=[(-1, 2), (0, 1.5)], log_scale=0.2),
+    'ks_resnet': dict(equation=_ks, ndims=2, nparams=0, ic=0.4, bc=None, domain=[(0, 3), (0, 1)],
+                      features=[7, 7, 7, 1], activation=['Tanh', Sin, 'Tanh'], layout='fa R fa+ R fa+ f',
+                      ranges=[(0, 3), (0, 1)]),
 }
 
 # problems that need the five- / six-direction kernels; the GPU tests of those kernels live in their own file
 HI_DIRECTION = ('hess3d', 'heat4d', 'lap6d', 'hess3d_var')
 # problems with derivatives of order 3 / 4 (whole-jet kernels); GPU tests in the same file
-HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate', 'biharmonic', 'kdv_icvar', 'kdv_silu', 'ks_gelu')
+HI_ORDER = ('kdv', 'beam', 'ks', 'ode3', 'plate', 'biharmonic', 'kdv_icvar', 'kdv_silu', 'ks_gelu', 'kdv_resnet', 'ks_resnet')
 
 GOLDEN_BATCH = {'poisson2d': 100, 'ode_param': 256, 'heat2d': 128, 'heat_param': 96, 'wave3d': 64,
                 'ode_var': 77, 'ode_tanh': 33, 'burgers': 130, 'nonlinear': 64, 'heat1d_icvar': 90, 'poisson_skip': 70, 'heat_resnet': 65, 'mixed2d': 80, 'mixed_ic': 75,
                 'poisson_sin': 85, 'heat_softplus': 72, 'burgers_silu': 66, 'wave1d_gelu': 91, 'mixed_acts_skip': 60,
                 'hess3d': 70, 'heat4d': 66, 'lap6d': 75, 'hess3d_var': 68,
                 'kdv': 72, 'beam': 69, 'ks': 65, 'ode3': 40, 'plate': 67, 'biharmonic': 71, 'kdv_icvar': 74,
-                'kdv_silu': 73, 'ks_gelu': 62}
+                'kdv_silu': 73, 'ks_gelu': 62, 'kdv_resnet': 70, 'ks_resnet': 61}
 
 # problems with a short recorded Adam trajectory: name -> (niters, batch, lr)
 GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'heat2d': (12, 64, 0.001),
@@ -286,7 +293,7 @@ GOLDEN_TRAJ = {'poisson2d': (40, 100, 0.005), 'ode_param': (25, 128, 0.01), 'hea
                'poisson_sin': (20, 64, 0.005), 'burgers_silu': (15, 48, 0.01), 'mixed_acts_skip': (12, 40, 0.01),
                'wave3d': (12, 96, 0.001), 'heat4d': (12, 48, 0.01), 'hess3d_var': (12, 40, 0.01),
                'kdv': (15, 48, 0.005), 'plate': (10, 40, 0.005), 'kdv_icvar': (15, 48, 0.01),
-               'kdv_silu': (15, 48, 0.005)}
+               'kdv_silu': (15, 48, 0.005), 'kdv_resnet': (15, 48, 0.005)}
 # (no trajectory for 'beam' and 'biharmonic': the reference's own fp32 fit is not reproducible there — nested autograd of
 #  order 4 returns losses of 1.78 and 921.7 (beam), 97.3 (biharmonic) at steps where fp64 gives 0.177, 0.169 and 5.86;
 #  tests/test_emul.py holds the fused math to the fp64 oracle along those fits instead)

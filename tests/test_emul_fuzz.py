@@ -271,7 +271,18 @@ def _random_high_order_problem(seed):
             ic = lambda *x: x[0] * (1.0 - x[-1]) * x[0] + 0.25 * torch.exp(-x[-1])
     bc = float(np.round(rng.uniform(-1, 1), 2)) if (nsp > 0 and rng.rand() < 0.6) else None
     domain = [(float(np.round(rng.uniform(-1, 0.2), 2)), float(np.round(rng.uniform(0.8, 2.5), 2))) for _ in range(ndims)]
-    return dict(ndims=ndims, nparams=nparams, total=total, features=widths + [1], acts=acts, layout='fa' * depth + 'f', ic=ic, bc=bc,
+    # residual blocks 'R fa+' (equal widths on both ends of the skip), possibly chained; drawn from a generator of its own
+    # so that the problems of the plain-chain seeds stay what they were
+    rng2 = np.random.RandomState(170000 + seed)
+    layout = 'fa'
+    for l in range(1, depth):
+        if rng2.rand() < 0.4:
+            widths[l] = widths[l - 1]
+            layout += ' R fa+'
+        else:
+            layout += ' fa'
+    layout += ' f'
+    return dict(ndims=ndims, nparams=nparams, total=total, features=widths + [1], acts=acts, layout=layout, ic=ic, bc=bc,
                 domain=domain, eq=eq, eq_name=name, ranges=domain + [(0.5, 2.0)] * nparams,
                 variables={'k': 0.7} if name == 'ode3var' else None, log_scale=float(np.round(rng.uniform(-0.5, 0.5), 2)))
 
