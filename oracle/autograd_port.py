@@ -170,11 +170,12 @@ class Problem:
         r = self.equation(u, *xs, D=D, V=self.V)
         return r, xs
 
-    def loss_and_grads(self, points):
-        """ -> (loss float, residual [B] ndarray, flat grads tensor) """
+    def loss_and_grads(self, points, criterion=None):
+        """ -> (loss float, residual [B] ndarray, flat grads tensor); `criterion(residual, zeros)` as in the
+        reference's fit (:448), default MSELoss """
         self.zero_grad()
         r, xs = self.residual(points)
-        loss = torch.nn.functional.mse_loss(r, torch.zeros_like(xs[0]))
+        loss = (criterion or torch.nn.functional.mse_loss)(r, torch.zeros_like(xs[0]))
         loss.backward()
         return float(loss.detach()), r.detach().reshape(-1).numpy().copy(), self.flat_grads()
 
@@ -189,7 +190,7 @@ def default_points(batch_size, total, dtype=torch.float32):
     return torch.cat([torch.rand((batch_size, 1)) for _ in range(total)], dim=1).to(dtype)
 
 
-def fit(problem, niters, batch_size, lr=0.005, optimizer='Adam', point_stream=None, **opt_kwargs):
+def fit(problem, niters, batch_size, lr=0.005, optimizer='Adam', point_stream=None, criterion=None, **opt_kwargs):
     """ The reference's training loop (:419-464) on the port.  `point_stream(i)` supplies the batch of
     iteration i ([B,total]); default: torch.rand per column like the reference.  Returns losses. """
     trainable = [p for p in problem.param_list() if p.requires_grad]
@@ -200,7 +201,7 @@ def fit(problem, niters, batch_size, lr=0.005, optimizer='Adam', point_stream=No
         pts = point_stream(i) if point_stream is not None else default_points(batch_size, problem.total,
                                                                               problem.dtype)
         r, xs = problem.residual(pts)
-        loss = torch.nn.functional.mse_loss(r, torch.zeros_like(xs[0]))
+        loss = (criterion or torch.nn.functional.mse_loss)(r, torch.zeros_like(xs[0]))
         loss.backward()
         opt.step()
         losses.append(float(loss.detach()))

@@ -94,6 +94,7 @@ class Solver:
 
         self._engine = None
         self._traced = None
+        self._crit_key = ('mse',)                         # criterion the traced programs (and the engine) are built for
         self._traced_constraints = {}                     # num -> (TracedEquation, points [n, total]) or None
         self._lower_error = None
         self._warned = False
@@ -137,7 +138,7 @@ class Solver:
 
             ic = model.raw_initial_condition
             self._traced = tracer.trace(self.equation, model.total, None, initial_condition=ic,
-                                        ndims_spatial=model.ndims_spatial, run=run)
+                                        ndims_spatial=model.ndims_spatial, run=run, criterion=self._crit_key)
             self._chain = chain
         except tracer.NotLowerable as exc:
             self._traced = None
@@ -168,7 +169,8 @@ class Solver:
                 try:
                     traced, args = tracer.trace_constraint(self.constraints[num], model.total,
                                                            initial_condition=model.raw_initial_condition,
-                                                           ndims_spatial=model.ndims_spatial, run=self._tracing_run)
+                                                           ndims_spatial=model.ndims_spatial, run=self._tracing_run,
+                                                           criterion=self._crit_key)
                     pts = self.reshape_and_concat(args).detach().to(torch.float32)
                     if pts.dim() != 2 or pts.shape[1] != model.total or pts.shape[0] < 1:
                         raise tracer.NotLowerable('constraint points do not have %d columns' % model.total)
@@ -201,15 +203,44 @@ class Solver:
                 raise
         return self._engine
 
+    @staticmethod
+    def _criterion_key(criterion):
+        """ The criteria the fused path trains with (reference :448 `criterion(residual, zeros)`): MSELoss natively;
+        L1Loss, HuberLoss and SmoothL1Loss through a residual transform (tracer.apply_criterion).  None: autograd. """
+        if getattr(criterion, 'reduction', None) != 'mean':
+            return None
+        kind = type(criterion)
+        if kind is nn.MSELoss:
+            return ('mse',)
+        if kind is nn.L1Loss:
+            return ('l1',)
+        if kind is nn.HuberLoss and float(criterion.delta) > 0:
+            return ('huber', float(criterion.delta))
+        if kind is nn.SmoothL1Loss and float(criterion.beta) >= 0:
+            return ('smooth_l1', float(criterion.beta)) if float(criterion.beta) > 0 else ('l1',)
+        return None
+
+    def _switch_criterion(self, key):
+        """ Re-trace equation and constraints for another criterion; the engine (plans, graphs, optimizer state) is
+        rebuilt on the next use — parameters keep their values. """
+        self._release_engine()
+        self._crit_key = key
+        self._traced_constraints = {}
+        self._lower_error = None
+        self._try_lower()
+
     def _fused_possible(self, criterion, loss_terms):
         if self.backend == 'torch':
             return False, 'backend="torch"'
-        if self._traced is None:
-            return False, self._lower_error
         if self.device.type != 'cuda':
             return False, 'device is %s' % self.device
-        if not (isinstance(criterion, nn.MSELoss) and criterion.reduction == 'mean'):
-            return False, 'criterion is not nn.MSELoss()'
+        key = self._criterion_key(criterion)
+        if key is None:
+            return False, 'criterion is not MSELoss / L1Loss / HuberLoss / SmoothL1Loss with mean reduction'
+        if key != self._crit_key:
+            self._switch_criterion(key)
+        if self._traced is None:
+            return False, self._lower_error
         if 'equation' not in loss_terms:
             return False, "'equation' is not among loss_terms"
         return True, None
@@ -255,7 +286,9 @@ class Solver:
                     in-kernel; anything else is sampled on the host and copied per step.
         loss_terms  'equation' and/or 'constraint_{k}' (reference :382-389).
         optimizer   name from torch.optim; None re-uses the existing optimizer (reference :391-393).
-        criterion   default nn.MSELoss(); anything else runs on the autograd path.
+        criterion   nn.MSELoss() (default), nn.L1Loss(), nn.HuberLoss(delta), nn.SmoothL1Loss(beta) with mean reduction
+                    train on the fused kernels (switching the criterion between fits rebuilds the engine); anything
+                    else runs on the autograd path.
         kwargs      forwarded to the optimizer constructor, except
                     steps_per_launch=k  (fused path, small batches): k whole optimizer steps — Adam included — per
                     launch of a persistent kernel.  Batches of at most 1024 points (the launch-bound regime of the

@@ -663,11 +663,44 @@ class TracedEquation:
         return 1 + self.nf * self.order if self.order > 2 else 1 + self.nf + self.ns
 
 
-def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0, run=None):
+CRITERION_EPS = 1e-30       # keeps sqrt(rho) differentiable at rho = 0 (a normal fp32 number; adds 1e-30 to the loss)
+
+
+def apply_criterion(res, criterion):
+    """ The kernels implement `MSELoss(residual, 0)` (reference model_torch.py:448 with its default criterion).  Any
+    other pointwise criterion rho >= 0 with mean reduction is brought to that form by training on the residual
+    r~ = sqrt(rho(r) + eps):  mean(r~^2) = mean(rho(r)) + eps, and the adjoint seed 2 r~ . dr~ = rho'(r) dr exactly —
+    the square root cancels, also in floating point up to rounding, and sign(0) = 0 gives torch's subgradient at r = 0.
+
+    criterion: None / ('mse',) | ('l1',) | ('huber', delta) | ('smooth_l1', beta)     (nn.L1Loss, nn.HuberLoss, nn.SmoothL1Loss)
+    min(|r|, delta) is written |r| - relu(|r| - delta) with relu(x) = (x + |x|) / 2, which is exact for |r| <= delta: small
+    residuals — where a fit ends up — do not lose digits against delta. """
+    if criterion is None or criterion[0] == 'mse':
+        return res
+    kind = criterion[0]
+    a = unary('abs', res)
+    if kind == 'l1' or (kind == 'smooth_l1' and float(criterion[1]) == 0.0):
+        rho = a
+    elif kind in ('huber', 'smooth_l1'):
+        delta = float(criterion[1])
+        if not delta > 0.0 or not math.isfinite(delta):
+            raise NotLowerable('criterion threshold %r' % (criterion[1],))
+        x = sub(a, const(delta))
+        m = sub(a, mul(const(0.5), add(x, unary('abs', x))))              # min(|r|, delta)
+        rho = mul(m, sub(a, mul(const(0.5), m)))                          # r^2 / 2 below delta, delta (|r| - delta / 2) above
+        if kind == 'smooth_l1':
+            rho = mul(const(1.0 / delta), rho)
+    else:
+        raise NotLowerable('criterion %r' % (kind,))
+    return unary('sqrt', add(rho, const(CRITERION_EPS)))
+
+
+def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0, run=None, criterion=None):
     """ Trace `equation(u, *xs)` (and `initial_condition(*x_spatial)` if callable).
 
     `var_factory(name)` is installed by the caller so that V(name, ...) returns `Sym(var(name))`
     during the trace.  `run` wraps the call (the Solver passes its contextvars ctx.run).
+    `criterion`: see apply_criterion (default: the residual itself, MSE).
     """
     run = run or (lambda f, *a: f(*a))
     xs = [Sym(coord(k)) for k in range(total)]
@@ -680,7 +713,7 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
 
     u_leaves = leaves(res, ('u',))
     if any(len(l.value) > 2 for l in u_leaves):
-        return _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run)
+        return _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run, criterion)
     first, second, mixed = set(), set(), set()
     for l in u_leaves:
         mi = l.value
@@ -719,7 +752,7 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
         d = len(axes2) + n
         mapping[uleaf((i, j))] = mul(const(0.5), sub(sub(chleaf(1 + nf + d), mapping[uleaf((i, i))]),
                                                      mapping[uleaf((j, j))]))
-    res = substitute(res, mapping)
+    res = apply_criterion(substitute(res, mapping), criterion)
     T.residual = res
     chan = {}
     by_channel = {c: chleaf(c) for c in range(C)}
@@ -765,7 +798,7 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
     return T
 
 
-def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run):
+def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spatial, run, criterion=None):
     """ Equations with derivatives of order 3 / 4 (D nested three / four times: u_xxx, u_xxxx): every direction carries
     its whole Taylor jet up to the highest order met (pinn_device_hi.cuh).  Directions are the differentiated
     arguments and, for every pair (i, j) with a mixed derivative, the two diagonals p = e_i + e_j and m = e_i - e_j,
@@ -818,6 +851,7 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
     res = substitute(res, mapping)
     if leaves(res, ('u',)):
         raise NotLowerable('a derivative of the equation has no jet channel')
+    res = apply_criterion(res, criterion)
     T.residual = res
 
     ic = None
@@ -860,7 +894,7 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
     return T
 
 
-def trace_constraint(constraint, total, initial_condition=None, ndims_spatial=0, run=None):
+def trace_constraint(constraint, total, initial_condition=None, ndims_spatial=0, run=None, criterion=None):
     """ Trace a constraint `constraint(u, *xs)` (reference model_torch.py:451-457: `u` is a callable that
     evaluates the model at user points, the value is driven to zero by MSE) into the same program form as an
     equation.  Lowerable when the constraint evaluates the model ONCE, at concrete points, and combines that
@@ -879,7 +913,7 @@ def trace_constraint(constraint, total, initial_condition=None, ndims_spatial=0,
         return Sym(uleaf())
 
     traced = trace(lambda _u, *xs: constraint(u_at, *xs), total, None, initial_condition=initial_condition,
-                   ndims_spatial=ndims_spatial, run=run)
+                   ndims_spatial=ndims_spatial, run=run, criterion=criterion)
     if not calls:
         raise NotLowerable('constraint does not evaluate the model')
     if traced.nf:

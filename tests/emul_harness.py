@@ -30,19 +30,19 @@ def lib():
     return _lib
 
 
-def traced_problem(name):
+def traced_problem(name, criterion=None):
     cfg = P.PROBLEMS[name]
     total = cfg['ndims'] + cfg['nparams']
     nsp = cfg['ndims'] - 1 if P.has_ic(name) else cfg['ndims']
     sym_V = lambda n, init: T.Sym(T.var(n))
     eq = P.bind(name, T.sym_D, sym_V)
-    return T.trace(eq, total, None, initial_condition=P.make_ic(name, sym_V), ndims_spatial=nsp)
+    return T.trace(eq, total, None, initial_condition=P.make_ic(name, sym_V), ndims_spatial=nsp, criterion=criterion)
 
 
-def spec_for(name):
+def spec_for(name, criterion=None):
     cfg = P.PROBLEMS[name]
     total = cfg['ndims'] + cfg['nparams']
-    tr = traced_problem(name)
+    tr = traced_problem(name, criterion)
     widths = [total] + list(cfg['features'])
     acts, skips = P.layer_plan(name)
     dom = cfg['domain']

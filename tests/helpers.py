@@ -32,3 +32,14 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64).reshape(-1)
     b = np.asarray(b, dtype=np.float64).reshape(-1)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def criterion_case(kind, residual):
+    """ -> (tracer criterion key, the torch criterion it stands for); thresholds at the median |residual| of the
+    problem's golden so that both branches of Huber / SmoothL1 are met """
+    med = float(np.float32(np.median(np.abs(residual))))
+    return {'l1': (('l1',), torch.nn.L1Loss()),
+            'huber': (('huber', med), torch.nn.HuberLoss(delta=med)),
+            'huber_default': (('huber', 1.0), torch.nn.HuberLoss()),
+            'smooth_l1': (('smooth_l1', med), torch.nn.SmoothL1Loss(beta=med)),
+            'smooth_l1_zero': (('smooth_l1', 0.0), torch.nn.SmoothL1Loss(beta=0.0))}[kind]

@@ -147,3 +147,36 @@ def test_constraints_lower_to_fused_launches_when_pointwise():
     assert s._lower_constraint(2) is None and s._lower_constraint(3) is None
     s.fit(niters=2, batch_size=8, loss_terms=['equation', 'constraint_0', 'constraint_2'])   # CPU: autograd path
     assert len(s.losses) == 2
+
+
+def test_criteria_other_than_mse():
+    """ reference :365 / :448 `criterion`: MSELoss, L1Loss, HuberLoss, SmoothL1Loss (mean reduction) have a fused form —
+    the Solver re-traces equation and constraints for the criterion of the fit; anything else stays on autograd.  On the
+    CPU the autograd path applies the criterion as the reference does. """
+    from torch import nn
+    key = Solver._criterion_key
+    assert key(nn.MSELoss()) == ('mse',) and key(nn.L1Loss()) == ('l1',)
+    assert key(nn.HuberLoss(delta=0.25)) == ('huber', 0.25) and key(nn.SmoothL1Loss(beta=0.5)) == ('smooth_l1', 0.5)
+    assert key(nn.SmoothL1Loss(beta=0.0)) == ('l1',)
+    assert key(nn.MSELoss(reduction='sum')) is None and key(nn.BCELoss()) is None and key(lambda a, b: (a - b).abs().mean()) is None
+
+    torch.manual_seed(0)
+    solver = Solver(lambda u, t: D(u, t) - 2 * np.pi * torch.cos(2 * np.pi * t), ndims=1, initial_condition=1,
+                    constraints=lambda u, t: u(torch.tensor([0.5])) - 1.0, layout='fa fa f', units=[8, 8, 1], activation='Tanh',
+                    device='cpu')
+    mse_prog = solver._traced.eq_prog
+    assert solver._lower_constraint(0) is not None
+    solver._switch_criterion(('huber', 0.5))
+    assert solver._crit_key == ('huber', 0.5) and solver._traced is not None and solver._traced_constraints == {}
+    assert len(solver._traced.eq_prog) > len(mse_prog)          # the residual transform is part of the program
+    assert solver._lower_constraint(0) is not None                     # constraints follow the criterion
+    from pydens_b200 import _native as N
+    tr = solver._traced
+    spec = N.build_spec([1, 8, 8, 1], ['tanh', 'tanh', 'none'], 1, 0, False, 0.0, True, [(0.0, 1.0)], tr)
+    assert spec.n_eq == len(tr.eq_prog)
+    solver._switch_criterion(('mse',))
+    assert len(solver._traced.eq_prog) == len(mse_prog)
+    for crit in (nn.L1Loss(), nn.HuberLoss(delta=0.3)):
+        before = len(solver.losses)
+        solver.fit(niters=3, batch_size=32, criterion=crit, loss_terms=('equation', 'constraint_0'))
+        assert len(solver.losses) == before + 3 and np.isfinite(solver.losses[-1])

@@ -7,7 +7,7 @@ import torch
 
 import problems as P
 import emul_harness as E
-from helpers import load_golden, oracle_problem, rel_l2
+from helpers import load_golden, oracle_problem, rel_l2, criterion_case
 
 
 def reference_fp32_error(name, g):
@@ -168,3 +168,38 @@ def test_traced_constraint_runs_as_a_plan_without_derivative_channels():
         T.trace_constraint(lambda u, x, t: u(0.1, 0.2) * x, 2)                  # mixes in the batch points
     with pytest.raises(T.NotLowerable):
         T.trace_constraint(lambda u, x, t: T.sym_D(u(0.1, 0.2) * x, x), 2)
+
+
+CRITERIA = ['l1', 'huber', 'huber_default', 'smooth_l1', 'smooth_l1_zero']
+
+
+@pytest.mark.parametrize('kind', CRITERIA)
+@pytest.mark.parametrize('name', ['poisson2d', 'burgers', 'heat1d_icvar', 'mixed_acts_skip', 'hess3d_var', 'kdv', 'ks_resnet'])
+def test_other_criteria_ride_on_the_mse_kernels(name, kind):
+    """ reference model_torch.py:448 `criterion(residual, zeros)` with a criterion other than MSELoss: the tracer trains
+    on sqrt(rho(r) + eps), so that the kernels' MSE is mean(rho) and their adjoint seed rho'(r) — loss and every gradient
+    against torch's own L1Loss / HuberLoss / SmoothL1Loss on the fp64 oracle, with residuals on both sides of the
+    threshold. """
+    g = load_golden(name)
+    key, crit = criterion_case(kind, g['residual'])
+    spec = E.spec_for(name, criterion=key)
+    loss, _, grads = E.emul_step(spec, g['params'], g['points'])
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    l64, r64, g64 = prob.loss_and_grads(g['points'].astype(np.float64), criterion=crit)
+    assert abs(loss - l64) <= 2e-5 * abs(l64)
+    assert rel_l2(grads, g64.numpy()) <= 1e-4
+
+
+def test_criterion_gradient_at_zero_residual_is_zero_not_nan():
+    """ r = 0 exactly (an equation the initial network already solves): L1 / Huber give a finite loss of eps and a zero
+    gradient (torch's subgradient at 0), not 0 * inf. """
+    from pydens_b200 import tracer as T, _native as N
+    for key in (('l1',), ('huber', 1.0), ('smooth_l1', 0.5)):
+        tr = T.trace(lambda u, x: (T.sym_D(u, x) - T.sym_D(u, x)) * u, 1, None, criterion=key)
+        spec = N.build_spec([1, 4, 1], ['tanh', 'none'], 1, 0, False, 0.0, False, [(0.0, 1.0)], tr)
+        rng = np.random.RandomState(0)
+        params = np.zeros(spec.n_params, dtype=np.float32)
+        params[:] = rng.uniform(-1, 1, size=spec.n_params)
+        loss, res, grads = E.emul_step(spec, params, rng.uniform(size=(40, 1)).astype(np.float32))
+        assert np.isfinite(grads).all() and np.abs(grads).max() == 0.0
+        assert 0.0 <= loss <= 1e-29

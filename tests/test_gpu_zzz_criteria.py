@@ -1,0 +1,67 @@
+""" Criteria other than MSELoss on the GPU (reference model_torch.py:365, :448 `criterion(residual, zeros)`): L1Loss,
+HuberLoss and SmoothL1Loss train on the same kernels through the residual transform of tracer.apply_criterion —
+through the bare C ABI against torch's own criteria on the fp64 oracle (thread kernel, tcgen05 tile kernel, whole-jet
+kernel), and through Solver.fit against the oracle port of the reference loop on identical batches.  (Sorted last: this
+joined after the round's GPU time was spent; its CPU twin is test_emul.py::test_other_criteria_ride_on_the_mse_kernels.) """
+import numpy as np
+import pytest
+import torch
+
+import problems as P
+import emul_harness as E
+from helpers import load_golden, oracle_problem, rel_l2, criterion_case
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gpu_helpers import make_solver, Replay, abi_step
+    from oracle import autograd_port as ap
+
+
+@pytest.mark.parametrize('kind', ['l1', 'huber', 'smooth_l1'])
+@pytest.mark.parametrize('name', ['poisson2d', 'burgers', 'heat1d_icvar', 'mixed_acts_skip', 'wave3d', 'kdv'])
+def test_step_with_other_criteria_matches_torch_criteria_on_the_fp64_oracle(name, kind):
+    g = load_golden(name)
+    key, crit = criterion_case(kind, g['residual'])
+    spec = E.spec_for(name, criterion=key)
+    loss, _, grads, u = abi_step(spec, g['params'], g['points'])
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    l64, _, g64 = prob.loss_and_grads(g['points'].astype(np.float64), criterion=crit)
+    assert abs(loss - l64) <= 2e-5 * abs(l64)
+    assert rel_l2(grads, g64.numpy()) <= 1e-4
+    assert rel_l2(u, g['u']) <= 1e-5
+
+
+@pytest.mark.parametrize('make', [lambda: torch.nn.HuberLoss(delta=0.05), lambda: torch.nn.L1Loss(),
+                                  lambda: torch.nn.SmoothL1Loss(beta=0.1)], ids=['huber', 'l1', 'smooth_l1'])
+def test_fit_with_other_criteria_follows_the_reference_loop(make):
+    """ Solver.fit(criterion=...) on the fused path against the oracle port of the reference loop (fp64, same criterion,
+    identical initial weights and batches); then back to MSELoss on the same Solver: the engine is rebuilt for the
+    criterion of the fit and the parameters carry over. """
+    name, niters, batch, lr = 'burgers', 20, 64, 0.01
+    g = load_golden(name)
+    solver = make_solver(name, g['params'])
+    batches = [P.make_points(name, batch, seed=1000 + i) for i in range(niters)]
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    ref = ap.fit(prob, niters, batch, lr=lr, criterion=make(),
+                 point_stream=lambda i: torch.from_numpy(batches[i].astype(np.float64)))
+    solver.fit(niters=niters, batch_size=batch, sampler=Replay(batches), lr=lr, criterion=make())
+    assert solver._engine is not None and solver._crit_key[0] != 'mse'
+    losses = np.asarray(solver.losses, dtype=np.float64)
+    assert losses.shape == ref.shape
+    assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-3
+    final, want = solver.flat_params().cpu().numpy(), prob.flat_params().numpy()
+    assert np.linalg.norm(final[:want.size] - want) / np.linalg.norm(want) <= 2e-3
+    first = solver._engine
+    solver.fit(niters=8, batch_size=batch, lr=lr)                       # MSELoss again, in-kernel sampling
+    assert solver._crit_key == ('mse',) and solver._engine is not None and solver._engine is not first
+    assert len(solver.losses) == niters + 8 and np.isfinite(np.asarray(solver.losses, dtype=np.float64)).all()
+    after = solver.flat_params().cpu().numpy()
+    assert np.linalg.norm(after - final) / np.linalg.norm(final) < 0.5   # continued from the Huber fit, not from scratch
+
+
+def test_unsupported_criterion_takes_the_autograd_path_loudly():
+    solver = make_solver('poisson2d', backend='auto')
+    with pytest.warns(UserWarning):
+        solver.fit(niters=2, batch_size=32, criterion=torch.nn.MSELoss(reduction='sum'))
+    assert len(solver.losses) == 2
