@@ -243,9 +243,13 @@ class FusedEngine:
         _native.check(self.lib.pinn_step(
             entry['plan'], C.c_void_p(self.flat.data_ptr()), C.c_void_p(entry['points'].data_ptr()), None,
             C.c_uint64(self.seed), None, C.c_uint64(0), C.c_uint64(0), C.c_int64(entry['n']),
-            C.c_float(1.0 / entry['n']), C.c_void_p(entry['out'].data_ptr()), None,
+            C.c_float(1.0 if self._sum_reduction() else 1.0 / entry['n']), C.c_void_p(entry['out'].data_ptr()), None,
             C.c_void_p(entry['workspace'].data_ptr()), C.c_size_t(entry['workspace'].numel()), self._stream()))
         self.out.add_(entry['out'])                       # [grads | loss] += the constraint's
+
+    def _sum_reduction(self):
+        """ criterion(reduction='sum') of the fit this engine was built for (Solver._crit_key ends with 'sum') """
+        return getattr(self.solver, '_crit_key', ('mse',))[-1] == 'sum'
 
     def release(self):
         """ Give every parameter its own storage back (the autograd path is taking over). """
@@ -468,7 +472,7 @@ class FusedEngine:
         if steps_per_launch > 0 and niters > 0:
             g = opt.param_groups[0] if opt.param_groups else {}
             ok = (type(opt) is torch.optim.Adam and len(opt.param_groups) == 1 and not g.get('amsgrad') and not g.get('maximize')
-                  and not torch.is_tensor(g.get('lr'))
+                  and not torch.is_tensor(g.get('lr')) and not self._sum_reduction()
                   and _dist() is None and not solver._constraint_numbers(loss_terms)
                   and 0 < batch_size <= self.lib.pinn_multi_step_max_points(self.plan))
             if not ok and not requested:
@@ -496,7 +500,9 @@ class FusedEngine:
         local_n, point_offset = shard_batch(batch_size, world, rank)
         if local_n <= 0:
             raise ValueError('batch_size %d is smaller than the number of ranks %d' % (batch_size, world))
-        inv_n = 1.0 / float(batch_size)
+        # weight of a point's criterion value in the loss: 1 / (global batch) — the mean of model_torch.py:448 —, or 1 for
+        # criteria with reduction='sum'
+        inv_n = 1.0 if self._sum_reduction() else 1.0 / float(batch_size)
         total = solver.model.total
         if niters <= 0:
             return

@@ -207,17 +207,26 @@ class Solver:
     def _criterion_key(criterion):
         """ The criteria the fused path trains with (reference :448 `criterion(residual, zeros)`): MSELoss natively;
         L1Loss, HuberLoss and SmoothL1Loss through a residual transform (tracer.apply_criterion).  None: autograd. """
-        if getattr(criterion, 'reduction', None) != 'mean':
+        functional = {nn.functional.mse_loss: ('mse',), nn.functional.l1_loss: ('l1',),
+                      nn.functional.huber_loss: ('huber', 1.0), nn.functional.smooth_l1_loss: ('smooth_l1', 1.0)}
+        try:
+            if criterion in functional:                   # the plain functions, with their defaults (mean reduction)
+                return functional[criterion]
+        except TypeError:                                 # unhashable callable
+            pass
+        reduction = getattr(criterion, 'reduction', None)
+        if reduction not in ('mean', 'sum'):
             return None
+        tail = ('sum',) if reduction == 'sum' else ()     # 'sum': the same kernels with weight 1 instead of 1 / batch_size
         kind = type(criterion)
         if kind is nn.MSELoss:
-            return ('mse',)
+            return ('mse',) + tail
         if kind is nn.L1Loss:
-            return ('l1',)
+            return ('l1',) + tail
         if kind is nn.HuberLoss and float(criterion.delta) > 0:
-            return ('huber', float(criterion.delta))
+            return ('huber', float(criterion.delta)) + tail
         if kind is nn.SmoothL1Loss and float(criterion.beta) >= 0:
-            return ('smooth_l1', float(criterion.beta)) if float(criterion.beta) > 0 else ('l1',)
+            return (('smooth_l1', float(criterion.beta)) if float(criterion.beta) > 0 else ('l1',)) + tail
         return None
 
     def _switch_criterion(self, key):
@@ -236,7 +245,7 @@ class Solver:
             return False, 'device is %s' % self.device
         key = self._criterion_key(criterion)
         if key is None:
-            return False, 'criterion is not MSELoss / L1Loss / HuberLoss / SmoothL1Loss with mean reduction'
+            return False, 'criterion is not MSELoss / L1Loss / HuberLoss / SmoothL1Loss (mean or sum reduction)'
         if key != self._crit_key:
             self._switch_criterion(key)
         if self._traced is None:
@@ -286,7 +295,7 @@ class Solver:
                     in-kernel; anything else is sampled on the host and copied per step.
         loss_terms  'equation' and/or 'constraint_{k}' (reference :382-389).
         optimizer   name from torch.optim; None re-uses the existing optimizer (reference :391-393).
-        criterion   nn.MSELoss() (default), nn.L1Loss(), nn.HuberLoss(delta), nn.SmoothL1Loss(beta) with mean reduction
+        criterion   nn.MSELoss() (default), nn.L1Loss(), nn.HuberLoss(delta), nn.SmoothL1Loss(beta), mean or sum reduction,
                     train on the fused kernels (switching the criterion between fits rebuilds the engine); anything
                     else runs on the autograd path.
         kwargs      forwarded to the optimizer constructor, except

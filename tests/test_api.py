@@ -158,7 +158,9 @@ def test_criteria_other_than_mse():
     assert key(nn.MSELoss()) == ('mse',) and key(nn.L1Loss()) == ('l1',)
     assert key(nn.HuberLoss(delta=0.25)) == ('huber', 0.25) and key(nn.SmoothL1Loss(beta=0.5)) == ('smooth_l1', 0.5)
     assert key(nn.SmoothL1Loss(beta=0.0)) == ('l1',)
-    assert key(nn.MSELoss(reduction='sum')) is None and key(nn.BCELoss()) is None and key(lambda a, b: (a - b).abs().mean()) is None
+    assert key(nn.functional.l1_loss) == ('l1',) and key(nn.functional.huber_loss) == ('huber', 1.0) and key(nn.functional.mse_loss) == ('mse',)
+    assert key(nn.MSELoss(reduction='sum')) == ('mse', 'sum') and key(nn.HuberLoss(reduction='sum', delta=2.0)) == ('huber', 2.0, 'sum')
+    assert key(nn.MSELoss(reduction='none')) is None and key(nn.BCELoss()) is None and key(lambda a, b: (a - b).abs().mean()) is None
 
     torch.manual_seed(0)
     solver = Solver(lambda u, t: D(u, t) - 2 * np.pi * torch.cos(2 * np.pi * t), ndims=1, initial_condition=1,
