@@ -695,6 +695,18 @@ def apply_criterion(res, criterion):
     return unary('sqrt', add(rho, const(CRITERION_EPS)))
 
 
+def criterion_outputs(res, partials, criterion):
+    """ Outputs of a residual program under a criterion: [r~] + [dr~/dr * p for p in partials], `partials` being the
+    partials of the untransformed residual `res`.  dr~/dr is differentiated ONCE, on a placeholder leaf, and shared by
+    all partials (instead of pushing every partial through the transform's product and quotient rules). """
+    if criterion is None or criterion[0] == 'mse':
+        return [res] + list(partials)
+    z = var('__residual__')
+    g = apply_criterion(z, criterion)
+    gp = substitute(diff_leaf(g, z), {z: res})
+    return [substitute(g, {z: res})] + [mul(gp, p) for p in partials]
+
+
 def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0, run=None, criterion=None):
     """ Trace `equation(u, *xs)` (and `initial_condition(*x_spatial)` if callable).
 
@@ -752,8 +764,8 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
         d = len(axes2) + n
         mapping[uleaf((i, j))] = mul(const(0.5), sub(sub(chleaf(1 + nf + d), mapping[uleaf((i, i))]),
                                                      mapping[uleaf((j, j))]))
-    res = apply_criterion(substitute(res, mapping), criterion)
-    T.residual = res
+    res = substitute(res, mapping)
+    T.residual = apply_criterion(res, criterion)
     chan = {}
     by_channel = {c: chleaf(c) for c in range(C)}
 
@@ -773,7 +785,8 @@ def trace(equation, total, var_factory, initial_condition=None, ndims_spatial=0,
         raise NotLowerable('more than 4 trainable variables')
     var_index = {n: i for i, n in enumerate(T.var_names)}
 
-    outputs = [res] + [diff_leaf(res, by_channel[c]) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
+    outputs = criterion_outputs(res, [diff_leaf(res, by_channel[c]) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names],
+                                criterion)
     T.eq_prog = lower(outputs, chan, var_index, C)
     T.n_slots = T.eq_prog.n_slots
 
@@ -851,8 +864,7 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
     res = substitute(res, mapping)
     if leaves(res, ('u',)):
         raise NotLowerable('a derivative of the equation has no jet channel')
-    res = apply_criterion(res, criterion)
-    T.residual = res
+    T.residual = apply_criterion(res, criterion)
 
     ic = None
     if initial_condition is not None:
@@ -870,7 +882,8 @@ def _trace_high_order(T, res, u_leaves, xs, total, initial_condition, ndims_spat
     if 1 + C + len(T.var_names) > 2 + 2 * MAX_DIRS + 4 or (ic_vars and C * (1 + len(T.var_names)) > (1 + 2 * MAX_DIRS) * 5):
         raise NotLowerable('%d jet channels and %d variables exceed the outputs of a residual program' % (C, len(T.var_names)))
     var_index = {n: i for i, n in enumerate(T.var_names)}
-    outputs = [res] + [diff_leaf(res, chleaf(c)) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names]
+    outputs = criterion_outputs(res, [diff_leaf(res, chleaf(c)) for c in range(C)] + [diff_leaf(res, var(n)) for n in T.var_names],
+                                criterion)
     T.eq_prog = lower(outputs, {}, var_index, C)
     T.n_slots = T.eq_prog.n_slots
     if ic is not None:
