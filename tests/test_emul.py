@@ -203,3 +203,34 @@ def test_criterion_gradient_at_zero_residual_is_zero_not_nan():
         loss, res, grads = E.emul_step(spec, params, rng.uniform(size=(40, 1)).astype(np.float32))
         assert np.isfinite(grads).all() and np.abs(grads).max() == 0.0
         assert 0.0 <= loss <= 1e-29
+
+
+@pytest.mark.parametrize('key,make', [(('huber', 0.05), lambda: torch.nn.HuberLoss(delta=0.05)), (('l1',), lambda: torch.nn.L1Loss()),
+                                      (('smooth_l1', 0.1), lambda: torch.nn.SmoothL1Loss(beta=0.1)),
+                                      (('mse', 'sum'), lambda: torch.nn.MSELoss(reduction='sum')),
+                                      (('huber', 0.05, 'sum'), lambda: torch.nn.HuberLoss(delta=0.05, reduction='sum'))],
+                         ids=['huber', 'l1', 'smooth_l1', 'mse_sum', 'huber_sum'])
+def test_emulated_fit_with_other_criteria_follows_the_reference_loop(key, make):
+    """ CPU twin of tests/test_gpu_zzz_criteria.py: the loop with the device math (host build) on the criterion's
+    residual program and the oracle's Adam, against the oracle port of the reference loop with torch's own criterion in
+    fp64, identical weights and batches.  reduction='sum' is the same program with point weight 1 instead of 1 / B. """
+    from oracle import autograd_port as ap
+    from oracle.adam import adam_step
+    name, niters, batch, lr = 'burgers', 20, 64, 0.01
+    g = load_golden(name)
+    batches = [P.make_points(name, batch, seed=1000 + i) for i in range(niters)]
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    ref = ap.fit(prob, niters, batch, lr=lr, criterion=make(),
+                 point_stream=lambda i: torch.from_numpy(batches[i].astype(np.float64)))
+    spec = E.spec_for(name, criterion=key)
+    weight = np.float32(batch if key[-1] == 'sum' else 1.0)
+    params = g['params'].astype(np.float32).copy()
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    losses = []
+    for i in range(niters):
+        loss, _, grads = E.emul_step(spec, params, batches[i])
+        losses.append(loss * weight)
+        adam_step(params, grads * weight, m, v, i + 1, lr=lr)
+    losses, want = np.asarray(losses, dtype=np.float64), prob.flat_params().numpy()
+    assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-4
+    assert np.linalg.norm(params[:want.size] - want) / np.linalg.norm(want) <= 2e-4
