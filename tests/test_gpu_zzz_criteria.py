@@ -11,7 +11,8 @@ import problems as P
 import emul_harness as E
 from helpers import load_golden, oracle_problem, rel_l2, criterion_case
 
-pytestmark = pytest.mark.gpu
+# a hang in a kernel that has not met a GPU yet must end as a failure of that test, not stall the whole tier
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 if torch.cuda.is_available():
     from gpu_helpers import make_solver, Replay, abi_step
