@@ -491,6 +491,7 @@ class FusedEngine:
             self._drop_graphs()
             self._opt_obj, self._opt_key = solver.optimizer, None
         nums = solver._constraint_numbers(loss_terms)
+        eq_term = 'equation' in loss_terms                # reference :448: the equation term is optional (:382-389)
         fused_constraints = [e for e in (self._constraint_plan(n) for n in nums) if e is not None]
         fused_nums = tuple(n for n in nums if self._constraint_plan(n) is not None)
         nums = [n for n in nums if self._constraint_plan(n) is None]     # the rest is added by autograd
@@ -523,7 +524,7 @@ class FusedEngine:
         fused_adam = (os.environ.get('PYDENS_B200_FUSED_ADAM', '1') != '0' and type(opt) is torch.optim.Adam
                       and len(opt.param_groups) == 1 and bool(g0.get('capturable')) and not g0.get('amsgrad')
                       and not g0.get('maximize') and not torch.is_tensor(g0.get('lr'))
-                      and not fused_constraints and not nums and not stray_params
+                      and not fused_constraints and not nums and not stray_params and eq_term
                       and (dist is None or self.comm is not None))
         adam, adam_key = None, None
         if fused_adam:
@@ -572,9 +573,12 @@ class FusedEngine:
             if fused_adam:
                 self._step_adam(points, cols, local_n, inv_n, point_offset, adam, allreduce=dist is not None)
                 return
-            self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
-            if dist is not None and self.comm is None:
-                dist.all_reduce(self.out)              # no peer-memory path: NCCL sums [grads | loss]
+            if eq_term:
+                self._step(points, cols, local_n, inv_n, point_offset, allreduce=dist is not None)
+                if dist is not None and self.comm is None:
+                    dist.all_reduce(self.out)          # no peer-memory path: NCCL sums [grads | loss]
+            else:
+                self.out.zero_()                       # loss_terms without 'equation': the constraint terms alone
             for entry in fused_constraints:            # after the all-reduce: every rank adds the same term
                 self._constraint_step(entry)
             if nums:

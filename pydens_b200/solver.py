@@ -250,8 +250,8 @@ class Solver:
             self._switch_criterion(key)
         if self._traced is None:
             return False, self._lower_error
-        if 'equation' not in loss_terms:
-            return False, "'equation' is not among loss_terms"
+        if 'equation' not in loss_terms and not self._constraint_numbers(loss_terms):
+            return False, 'no loss term'                  # the autograd path fails on it as the reference does
         return True, None
 
     # ------------------------------------------------------------------------------------------

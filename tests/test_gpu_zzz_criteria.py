@@ -68,3 +68,32 @@ def test_unsupported_criterion_takes_the_autograd_path_loudly():
     with pytest.warns(UserWarning):
         solver.fit(niters=2, batch_size=32, criterion=lambda a, b: ((a - b) ** 2).mean())
     assert len(solver.losses) == 2
+
+
+@pytest.mark.parametrize('fused_constraints', ['1', '0'])
+def test_constraint_only_fit_stays_on_the_engine_and_matches_autograd(fused_constraints, monkeypatch):
+    """ loss_terms without 'equation' (reference :382-389, :448-457): the step is the constraint terms alone — as fused
+    launches of the constraint plans, or as autograd terms inside the engine's loop — against the autograd backend. """
+    from pydens_b200 import Solver, D, V
+    monkeypatch.setenv('PYDENS_B200_FUSED_CONSTRAINTS', fused_constraints)
+
+    def odevar(u, t):
+        return D(u, t) - 2 * np.pi * torch.cos(2 * np.pi * t)
+
+    def initial(*args):
+        return V('init', data=torch.Tensor([3.0]))
+
+    def make(backend):
+        torch.manual_seed(0)
+        return Solver(odevar, ndims=1, initial_condition=initial, layout='fafaf', features=[12, 10, 1], activation='Tanh',
+                      constraints=lambda u, t: u(torch.tensor([0.5])) - 0.25, device='cuda', backend=backend)
+    fused, ref = make('fused'), make('torch')
+    ref.model.load_state_dict(fused.model.state_dict())
+    for s in (fused, ref):
+        s.fit(niters=30, batch_size=64, lr=0.02, loss_terms='constraint_0')
+    assert fused._engine is not None and (fused._engine._constraint_plans[0] is not None) == (fused_constraints == '1')
+    a, b = np.asarray(fused.losses, dtype=np.float64), np.asarray(ref.losses, dtype=np.float64)
+    assert a.shape == b.shape == (30,) and b[-1] < b[0]
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 2e-3
+    assert abs(float(fused.model.init.detach()) - float(ref.model.init.detach())) <= 1e-4
+    assert float(fused.model.init.detach()) != 3.0
