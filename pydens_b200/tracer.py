@@ -368,7 +368,33 @@ _REWRITES = {
     'exp2': lambda a: unary('exp', mul(const(math.log(2.0)), a)),
     'log2': lambda a: mul(const(1.0 / math.log(2.0)), unary('log', a)),
     'log10': lambda a: mul(const(1.0 / math.log(10.0)), unary('log', a)),
+    # piecewise-linear functions through |.|: exact where they are linear, torch's values everywhere, torch's
+    # derivatives except exactly at the kink (there: the mean of the one-sided ones)
+    'relu': lambda a: mul(const(0.5), add(a, unary('abs', a))),
+    'silu': lambda a: mul(a, unary('sigmoid', a)),
+    'softplus': lambda a: add(mul(const(0.5), add(a, unary('abs', a))),                     # max(a, 0) + log(1 + e^-|a|)
+                              unary('log', add(ONE, unary('exp', neg(unary('abs', a)))))),
 }
+
+
+def _maximum(a, b):
+    return mul(const(0.5), add(add(a, b), unary('abs', sub(a, b))))
+
+
+def _minimum(a, b):
+    return mul(const(0.5), sub(add(a, b), unary('abs', sub(a, b))))
+
+
+def _clamp(a, lo=None, hi=None):
+    if lo is not None:
+        a = _maximum(a, _as_expr(lo))
+    if hi is not None:
+        a = _minimum(a, _as_expr(hi))
+    return a
+
+
+_REWRITES2 = {'maximum': _maximum, 'minimum': _minimum, 'max': _maximum, 'min': _minimum, 'fmax': _maximum, 'fmin': _minimum,
+              'hypot': lambda a, b: unary('sqrt', add(powi(a, 2), powi(b, 2)))}
 
 
 class Sym:
@@ -410,6 +436,13 @@ class Sym:
     def reciprocal(self): return Sym(div(ONE, self.expr))
     def rsqrt(self): return Sym(_REWRITES['rsqrt'](self.expr))
     def neg(self): return Sym(neg(self.expr))
+    def relu(self): return Sym(_REWRITES['relu'](self.expr))
+    def clamp(self, min=None, max=None): return Sym(_clamp(self.expr, min, max))      # noqa: A002  (torch's own names)
+    clip = clamp
+    def clamp_min(self, min): return Sym(_clamp(self.expr, min, None))                 # noqa: A002
+    def clamp_max(self, max): return Sym(_clamp(self.expr, None, max))                 # noqa: A002
+    def maximum(self, o): return Sym(_maximum(self.expr, _as_expr(o)))
+    def minimum(self, o): return Sym(_minimum(self.expr, _as_expr(o)))
     def view(self, *shape): return self
     def reshape(self, *shape): return self
     def float(self): return self
@@ -440,6 +473,19 @@ class Sym:
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         name = getattr(func, '__name__', None)
+        if name in ('clamp', 'clip', 'clamp_min', 'clamp_max') and args and set(kwargs or ()) <= {'min', 'max'}:
+            rest = list(args[1:])
+            if name == 'clamp_max':
+                rest = [None] + rest
+            lo = (kwargs or {}).get('min', rest[0] if len(rest) > 0 else None)
+            hi = (kwargs or {}).get('max', rest[1] if len(rest) > 1 else None)
+            if len(rest) <= 2 and (lo is not None or hi is not None):
+                return Sym(_clamp(_as_expr(args[0]), lo, hi))
+        if kwargs and name in ('relu', 'silu', 'softplus', 'sigmoid', 'tanh'):
+            # torch.nn.functional passes its defaults on as keywords: those (and only those) are fine
+            defaults = {'inplace': False, 'beta': 1, 'threshold': 20}
+            if all(k in defaults and v == defaults[k] for k, v in kwargs.items()):
+                kwargs = None
         if kwargs:
             raise NotLowerable('keyword arguments to torch.%s while tracing' % name)
         if name in ('__add__', '__radd__'): name = 'add'
@@ -459,6 +505,8 @@ class Sym:
             return Sym(_TORCH_BINARY[name](_as_expr(args[0]), _as_expr(args[1])))
         if name in _REWRITES and len(args) == 1:
             return Sym(_REWRITES[name](_as_expr(args[0])))
+        if name in _REWRITES2 and len(args) == 2:
+            return Sym(_REWRITES2[name](_as_expr(args[0]), _as_expr(args[1])))
         if name in ('zeros_like', 'ones_like') and len(args) == 1:
             return Sym(ZERO if name == 'zeros_like' else ONE)
         raise NotLowerable('torch.%s is not supported by the fused path' % name)
@@ -472,6 +520,8 @@ class Sym:
             return Sym(_NP_BINARY[ufunc](_as_expr(inputs[0]), _as_expr(inputs[1])))
         if ufunc.__name__ in _REWRITES and len(inputs) == 1:
             return Sym(_REWRITES[ufunc.__name__](_as_expr(inputs[0])))
+        if ufunc.__name__ in _REWRITES2 and len(inputs) == 2:
+            return Sym(_REWRITES2[ufunc.__name__](_as_expr(inputs[0]), _as_expr(inputs[1])))
         raise NotLowerable('numpy.%s is not supported by the fused path' % ufunc.__name__)
 
 

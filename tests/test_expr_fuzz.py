@@ -228,3 +228,50 @@ def test_random_initial_condition_matches_autograd(seed):
     u = E.emul_forward(spec, params, pts)
     ref_u = prob.predict(pts.astype(np.float64))
     assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max())
+
+
+# functions that lower through |.| (relu, clamp, maximum / minimum, hypot, F.softplus, F.silu): tables of their own so
+# that the problems of the seeds above stay what they were
+PIECEWISE_UNARY = [
+    ('relu', lambda t: torch.relu(t)), ('clamp', lambda t: torch.clamp(t, -0.5, 0.8)), ('clamp_min', lambda t: torch.clamp(t, min=0.1)),
+    ('softplus', lambda t: torch.nn.functional.softplus(t)), ('silu', lambda t: torch.nn.functional.silu(t)),
+    ('relu_m', lambda t: (t - 0.3).relu()),
+]
+PIECEWISE_BINARY = [
+    ('maximum', lambda a, b: torch.maximum(a, b)), ('minimum', lambda a, b: torch.minimum(a, b)),
+    ('hypot', lambda a, b: torch.hypot(a, b + 0.5)),
+]
+
+
+@pytest.mark.parametrize('seed', list(range(60)))
+def test_random_expression_with_piecewise_functions_matches_autograd(seed, monkeypatch):
+    import sys
+    mod = sys.modules[__name__]
+    monkeypatch.setattr(mod, 'UNARY', UNARY + PIECEWISE_UNARY * 2)
+    monkeypatch.setattr(mod, 'BINARY', BINARY + PIECEWISE_BINARY)
+    rng = np.random.RandomState(15000 + seed)
+    total = int(rng.randint(1, 3))
+    eq, text, use_var = random_equation(rng, total)
+    features, acts = [6, 5, 1], ['Tanh', 'Sigmoid']
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    try:
+        traced = T.trace(lambda u, *xs: eq(u, *xs, D=T.sym_D, V=sym_V), total, None)
+    except T.NotLowerable as exc:
+        assert 'slots' in str(exc) or 'instructions' in str(exc) or 'directions' in str(exc), (text, exc)
+        return
+    spec = N.build_spec([total] + features, ['tanh', 'sigmoid', 'none'], total, 0, False, 0.0, False,
+                        [(0.0, 1.0)] * total, traced)
+    uses_var = 'k' in traced.var_names
+    if 'var' in text and not uses_var:
+        return
+    prob = ap.Problem(eq, ndims=total, features=features, activation=acts, dtype=torch.float64,
+                      variables={'k': 0.7} if uses_var else None, seed=seed, layout='fafaf')
+    params = prob.flat_params().numpy().astype(np.float32)
+    pts = rng.uniform(0.05, 0.95, size=(40, total)).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params, pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(ref_res)))), 1e-30))
+    assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
+    assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text

@@ -248,3 +248,39 @@ def test_rewritten_functions_match_torch():
     grads = torch.autograd.grad(r.sum(), ch)
     for c in range(3):
         assert np.allclose(outs[1 + c], grads[c].numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_piecewise_linear_functions_lower_through_abs():
+    """ relu / clamp / maximum / minimum / hypot / F.softplus / F.silu have no opcode of their own: they lower through
+    |.|, sigmoid, exp and log; values and partials must match torch's (away from the kinks, which the random points are). """
+    import torch.nn.functional as F
+
+    def eq(u, x, y, D=T.sym_D):
+        return (torch.relu(u - 0.2) * torch.clamp(x, min=0.3) + torch.clamp(D(u, x), -0.4, 0.5) - torch.maximum(u, y)
+                + torch.minimum(D(u, y), x - 0.5) * F.softplus(3.0 * u) + F.silu(D(u, x)) + torch.hypot(u, y + 0.1)
+                + (u * 2.0).clamp(max=0.7) - (x - u).relu() + np.maximum(u, 0.25) + torch.clamp_min(y - u, 0.1))
+    tr = T.trace(lambda u, x, y: eq(u, x, y), 2, None)
+    assert tr.nf == 2 and tr.ns == 0
+    rng = np.random.RandomState(4)
+    n = 200
+    jet = rng.uniform(-1, 1, size=(3, n))
+    coords = rng.uniform(0, 1, size=(2, n))
+    outs = T.run_program(tr.eq_prog, jet, coords, [])
+    ch = [torch.tensor(jet[c], dtype=torch.float64, requires_grad=True) for c in range(3)]
+    x, y = (torch.tensor(coords[k], dtype=torch.float64) for k in range(2))
+    col = {d: 1 + i for i, d in enumerate(tr.dirs)}
+
+    def D_num(v, xx):
+        return ch[col[0]] if xx is x else ch[col[1]]
+
+    def eq_t(u, x, y, D):                                    # the same expression with torch-only spellings
+        return (torch.relu(u - 0.2) * torch.clamp(x, min=0.3) + torch.clamp(D(u, x), -0.4, 0.5) - torch.maximum(u, y)
+                + torch.minimum(D(u, y), x - 0.5) * F.softplus(3.0 * u) + F.silu(D(u, x)) + torch.hypot(u, y + 0.1)
+                + (u * 2.0).clamp(max=0.7) - (x - u).relu() + torch.clamp(u, min=0.25) + torch.clamp_min(y - u, 0.1))
+    r = eq_t(ch[0], x, y, D_num)
+    assert np.allclose(outs[0], r.detach().numpy(), rtol=1e-12, atol=1e-12)
+    grads = torch.autograd.grad(r.sum(), ch)
+    for c in range(3):
+        assert np.allclose(outs[1 + c], grads[c].numpy(), rtol=1e-10, atol=1e-12)
+    with pytest.raises(T.NotLowerable):
+        T.trace(lambda u, x: F.softplus(u, beta=2.0) + x, 1, None)
