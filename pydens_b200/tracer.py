@@ -509,6 +509,8 @@ class Sym:
             return Sym(_REWRITES2[name](_as_expr(args[0]), _as_expr(args[1])))
         if name in ('zeros_like', 'ones_like') and len(args) == 1:
             return Sym(ZERO if name == 'zeros_like' else ONE)
+        if name == 'full_like' and len(args) == 2 and isinstance(args[1], numbers.Real):
+            return Sym(const(float(args[1])))
         raise NotLowerable('torch.%s is not supported by the fused path' % name)
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
