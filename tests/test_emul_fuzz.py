@@ -324,3 +324,60 @@ def test_random_high_order_problem_matches_fp64_oracle(seed):
     u = E.emul_forward(spec, params.astype(np.float32), pts)
     ref_u = prob.predict(pts.astype(np.float64))
     assert np.abs(u - ref_u).max() <= 1e-5 * max(1.0, np.abs(ref_u).max()), tag
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# criteria other than MSE (tracer.apply_criterion) on random problems of all three families
+# ---------------------------------------------------------------------------------------------------------------
+def _criterion_problem(seed):
+    rng = np.random.RandomState(250000 + seed)
+    family = int(rng.randint(3))
+    cfg = [_random_problem, _random_many_direction_problem, _random_high_order_problem][family](int(rng.randint(100000)))
+    kind = ['l1', 'huber', 'smooth_l1'][int(rng.randint(3))]
+    return cfg, kind, bool(rng.rand() < 0.3), int(rng.choice([5, 33, 70]))
+
+
+@pytest.mark.parametrize('seed', list(range(60)))
+def test_random_problem_with_other_criteria_matches_torch_criteria(seed):
+    cfg, kind, use_sum, n = _criterion_problem(seed)
+    sym_V = lambda n_, init: T.Sym(T.var(n_))
+    nsp = cfg['ndims'] - 1 if cfg['ic'] is not None else cfg['ndims']
+    nparams = cfg.get('nparams', 0)
+    prob = ap.Problem(cfg['eq'], ndims=cfg['ndims'], nparams=nparams, initial_condition=cfg['ic'],
+                      boundary_condition=cfg['bc'], domain=cfg['domain'], features=cfg['features'],
+                      activation=cfg['acts'] or 'Tanh', dtype=torch.float64, variables=cfg['variables'], seed=seed,
+                      layout=cfg['layout'])
+    with torch.no_grad():
+        prob.log_scale.fill_(cfg['log_scale'])
+    params = prob.flat_params().numpy().astype(np.float32)
+    rng = np.random.RandomState(260000 + seed)
+    # points at least 1e-3 of the width away from the faces: next to a face the ORACLE's nested torch.prod backward
+    # loses its digits (whole-jet paragraph)
+    pts = np.concatenate([rng.uniform(lo + 1e-3 * (hi - lo), hi - 1e-3 * (hi - lo), size=(n, 1)) for lo, hi in cfg['ranges']],
+                         axis=1).astype(np.float32)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    _, r64, _ = prob.loss_and_grads(pts.astype(np.float64))
+    thr = float(np.float32(np.median(np.abs(r64))))               # both branches of Huber / SmoothL1 are met
+    red = 'sum' if use_sum else 'mean'
+    key, crit = {'l1': (('l1',), torch.nn.L1Loss(reduction=red)),
+                 'huber': (('huber', thr), torch.nn.HuberLoss(delta=thr, reduction=red)),
+                 'smooth_l1': (('smooth_l1', thr), torch.nn.SmoothL1Loss(beta=thr, reduction=red))}[kind]
+    traced = T.trace(lambda u, *xs: cfg['eq'](u, *xs, D=T.sym_D, V=sym_V), cfg['total'], None,
+                     initial_condition=cfg['ic'], ndims_spatial=nsp, criterion=key)
+    acts, skips = _layer_plan(cfg)
+    spec = N.build_spec([cfg['total']] + cfg['features'], acts, cfg['ndims'], nparams, cfg['bc'] is not None,
+                        cfg['bc'] if cfg['bc'] is not None else 0.0, cfg['ic'] is not None, cfg['domain'], traced,
+                        skips=skips)
+    loss, _, grads = E.emul_step(spec, params, pts)
+    weight = float(n) if use_sum else 1.0
+    ref_loss, _, ref_grads = prob.loss_and_grads(pts.astype(np.float64), criterion=crit)
+    tag = '%s %s %s %s acts=%s n=%d' % (kind, red, cfg['eq_name'], cfg['layout'], acts, n)
+    # the criteria are not smooth: a residual within fp32 rounding of a kink (0 for L1, the threshold for the others)
+    # lands on the other branch in fp32 — its weight in the gradient is 1 / n, which bounds what one such point can do
+    near_kink = np.abs(np.abs(r64) - (0.0 if kind == 'l1' else thr)) <= 1e-5 * np.maximum(np.abs(r64), thr)
+    slack = 1.0 + 1e4 * float(near_kink.mean()) * (1.0 if kind == 'l1' else 1e-5)
+    cond = max(1.0, 0.05 / max(float(np.sqrt(np.mean(np.square(r64)))), 1e-30))
+    if cfg['eq_name'] in ('biharmonic', 'mixed3'):
+        cond *= 5.0
+    assert abs(loss * weight - ref_loss) <= 2e-5 * cond * max(abs(ref_loss), 1e-6), tag
+    assert rel_l2(grads * np.float32(weight), ref_grads.numpy()) <= 1e-4 * cond * slack, tag
