@@ -393,6 +393,34 @@ def _clamp(a, lo=None, hi=None):
     return a
 
 
+_FINITE_KINDS = ('const', 'coord', 'u', 'var', 'ch', 'add', 'sub', 'mul', 'neg', 'sin', 'cos', 'tanh', 'sigmoid', 'abs', 'sign')
+
+
+def _always_finite(e, seen=None):
+    """ True when `e` cannot evaluate to inf / NaN on finite inputs short of overflow of a polynomial: sums, products,
+    bounded functions, non-negative integer powers.  (exp, log, sqrt, /, ** and tan are not in that set.) """
+    seen = set() if seen is None else seen
+    if e in seen:
+        return True
+    seen.add(e)
+    if e.kind == 'powi':
+        return e.value >= 0 and _always_finite(e.args[0], seen)
+    if e.kind not in _FINITE_KINDS:
+        return False
+    return all(_always_finite(a, seen) for a in e.args)
+
+
+def _where(condition, a, b):
+    """ torch.where(condition, a, b) as c a + (1 - c) b with the 0 / 1 indicator c of the condition: exact for c in {0, 1}
+    provided the branch that is NOT selected is finite — torch.where is often the guard around a branch that is not
+    (sqrt of a negative number, a division by zero), and 0 * NaN is NaN: such branches stay on autograd. """
+    c = Sym._indicator_expr(condition)
+    a, b = _as_expr(a), _as_expr(b)
+    if not (_always_finite(a) and _always_finite(b)):
+        raise NotLowerable('torch.where with a branch that may not be finite where it is not selected')
+    return add(mul(c, a), mul(sub(ONE, c), b))
+
+
 _REWRITES2 = {'maximum': _maximum, 'minimum': _minimum, 'max': _maximum, 'min': _minimum, 'fmax': _maximum, 'fmin': _minimum,
               'hypot': lambda a, b: unary('sqrt', add(powi(a, 2), powi(b, 2)))}
 
@@ -450,11 +478,57 @@ class Sym:
     def __bool__(self):
         raise NotLowerable('data-dependent control flow in a traced callable')
 
-    def _compare(self, other):
-        raise NotLowerable('comparisons (data-dependent control flow) in a traced callable')
+    # Order comparisons give the 0 / 1 indicator (1 + sign(a - b)) / 2 — what torch's bool tensor is once it meets
+    # arithmetic or torch.where, except ON the threshold (1/2 instead of 0 or 1: a set of measure zero for sampled
+    # points).  Its derivative is zero, as autograd's.  Indicators combine with & | ~ and select with torch.where;
+    # using one in an `if` still leaves the fused path (__bool__), and so does == / !=.
+    def _indicator(self, other, flip):
+        a, b = self.expr, _as_expr(other)
+        d = sub(b, a) if flip else sub(a, b)
+        out = Sym(mul(const(0.5), add(ONE, unary('sign', d))))
+        out.is_indicator = True
+        return out
 
-    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _compare
+    def __gt__(self, o): return self._indicator(o, False)
+    def __ge__(self, o): return self._indicator(o, False)
+    def __lt__(self, o): return self._indicator(o, True)
+    def __le__(self, o): return self._indicator(o, True)
+
+    def _compare(self, other):
+        raise NotLowerable('== / != (data-dependent control flow) in a traced callable')
+
+    __eq__ = __ne__ = _compare
     __hash__ = object.__hash__                 # defining __eq__ would otherwise make Sym unhashable
+
+    @staticmethod
+    def _indicator_expr(x):
+        if isinstance(x, Sym) and getattr(x, 'is_indicator', False):
+            return x.expr
+        if isinstance(x, (bool, np.bool_)):
+            return ONE if x else ZERO
+        if isinstance(x, torch.Tensor) and x.dtype == torch.bool and x.numel() == 1:
+            return ONE if bool(x) else ZERO
+        raise NotLowerable('boolean operation on something that is not a comparison of traced tensors')
+
+    def _logical(self, other, kind):
+        a, b = Sym._indicator_expr(self), Sym._indicator_expr(other)
+        out = Sym(mul(a, b) if kind == 'and' else sub(add(a, b), mul(a, b)) if kind == 'or'
+                  else sub(add(a, b), mul(const(2.0), mul(a, b))))
+        out.is_indicator = True
+        return out
+
+    def __and__(self, o): return self._logical(o, 'and')
+    def __or__(self, o): return self._logical(o, 'or')
+    def __xor__(self, o): return self._logical(o, 'xor')
+    __rand__, __ror__, __rxor__ = __and__, __or__, __xor__
+
+    def __invert__(self):
+        out = Sym(sub(ONE, Sym._indicator_expr(self)))
+        out.is_indicator = True
+        return out
+
+    def where(self, condition, other):
+        return Sym(_where(condition, self, other))
 
     # what a tensor would accept but a symbolic column cannot express: bail out of the fused path cleanly
     # (the reference runs such equations on autograd, model_torch.py:448) instead of raising a TypeError
@@ -462,7 +536,7 @@ class Sym:
         raise NotLowerable('indexing / integer arithmetic / len() on a traced tensor')
 
     __getitem__ = __setitem__ = __mod__ = __rmod__ = __floordiv__ = __rfloordiv__ = _unsupported
-    __len__ = __iter__ = __matmul__ = __rmatmul__ = __and__ = __or__ = __xor__ = __invert__ = _unsupported
+    __len__ = __iter__ = __matmul__ = __rmatmul__ = _unsupported
     __int__ = __float__ = __index__ = _unsupported
 
     def __getattr__(self, name):
@@ -507,6 +581,23 @@ class Sym:
             return Sym(_REWRITES[name](_as_expr(args[0])))
         if name in _REWRITES2 and len(args) == 2:
             return Sym(_REWRITES2[name](_as_expr(args[0]), _as_expr(args[1])))
+        if name == 'where' and len(args) == 3:
+            return Sym(_where(args[0], args[1], args[2]))
+        if name in ('gt', 'ge', 'lt', 'le', 'greater', 'greater_equal', 'less', 'less_equal') and len(args) == 2:
+            flip = name in ('lt', 'le', 'less', 'less_equal')
+            if isinstance(args[0], Sym):
+                return args[0]._indicator(args[1], flip)
+            return args[1]._indicator(args[0], not flip)
+        if name in ('logical_and', 'logical_or', 'logical_xor', '__and__', '__or__', '__xor__', '__rand__', '__ror__', '__rxor__') and len(args) == 2:
+            lhs = args[0] if isinstance(args[0], Sym) else args[1]
+            rhs = args[1] if isinstance(args[0], Sym) else args[0]
+            return lhs._logical(rhs, 'and' if 'and' in name else ('xor' if 'xor' in name else 'or'))
+        if name in ('logical_not', '__invert__') and len(args) == 1:
+            return args[0].__invert__()
+        if name in ('__gt__', '__ge__') and len(args) == 2:
+            return args[0]._indicator(args[1], False) if isinstance(args[0], Sym) else args[1]._indicator(args[0], True)
+        if name in ('__lt__', '__le__') and len(args) == 2:
+            return args[0]._indicator(args[1], True) if isinstance(args[0], Sym) else args[1]._indicator(args[0], False)
         if name in ('zeros_like', 'ones_like') and len(args) == 1:
             return Sym(ZERO if name == 'zeros_like' else ONE)
         if name == 'full_like' and len(args) == 2 and isinstance(args[1], numbers.Real):

@@ -275,3 +275,42 @@ def test_random_expression_with_piecewise_functions_matches_autograd(seed, monke
     assert abs(loss - ref_loss) <= 3e-5 * cond * max(abs(ref_loss), 1e-6), text
     assert rel_l2(residual, ref_res) <= 3e-5 * cond, text
     assert rel_l2(grads, ref_grads.numpy()) <= 1e-4 * cond, text
+
+
+def _interface_equations():
+    """ piecewise coefficients / sources whose conditions are on the coordinates (exact fp32 inputs: both precisions take
+    the same branch) """
+    def diffusivity(u, x, y, D, V):
+        a = torch.where(x < 0.5, 1.0, 10.0)
+        return a * D(D(u, x), x) + D(D(u, y), y) - torch.where((x > 0.2) & (y <= 0.7), torch.sin(3.0 * x), 0.0 * x)
+
+    def reaction(u, x, y, D, V):
+        k = torch.where(y > x, 2.0, 0.5) * V('k', 0.7)
+        return D(u, y) - D(D(u, x), x) + k * u * (1.0 - u) + (x > 0.6) * 0.3 - (~(y > 0.25)) * u
+
+    def third(u, x, y, D, V):
+        return D(u, y) + torch.where(x >= 0.4, 6.0, 1.5) * u * D(u, x) + D(D(D(u, x), x), x) * ((y < 0.5) | (x < 0.3))
+    return [('diffusivity', diffusivity, None), ('reaction', reaction, {'k': 0.7}), ('third', third, None)]
+
+
+@pytest.mark.parametrize('which', [0, 1, 2])
+def test_interface_problems_match_autograd(which):
+    """ torch.where / comparisons in the equation run as indicator arithmetic in the device interpreter (host build):
+    loss, residual and gradients against the fp64 oracle executing the user's torch.where. """
+    name, eq, variables = _interface_equations()[which]
+    features, acts = [8, 6, 1], ['Tanh', 'Sigmoid']
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    traced = T.trace(lambda u, *xs: eq(u, *xs, D=T.sym_D, V=sym_V), 2, None, initial_condition=0.3, ndims_spatial=1)
+    spec = N.build_spec([2] + features, ['tanh', 'sigmoid', 'none'], 2, 0, True, 0.1, True, [(0.0, 1.0)] * 2, traced)
+    prob = ap.Problem(eq, ndims=2, features=features, activation=acts, dtype=torch.float64, variables=variables, seed=which,
+                      layout='fafaf', initial_condition=0.3, boundary_condition=0.1)
+    params = prob.flat_params().numpy().astype(np.float32)
+    assert spec.n_params == params.size
+    rng = np.random.RandomState(77 + which)
+    pts = rng.uniform(0.02, 0.98, size=(96, 2)).astype(np.float32)
+    loss, residual, grads = E.emul_step(spec, params, pts)
+    prob.load_flat(torch.from_numpy(params.astype(np.float64)))
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64))
+    assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss), name
+    assert rel_l2(residual, ref_res) <= 2e-5, name
+    assert rel_l2(grads, ref_grads.numpy()) <= 1e-4, name

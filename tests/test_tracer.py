@@ -284,3 +284,43 @@ def test_piecewise_linear_functions_lower_through_abs():
         assert np.allclose(outs[1 + c], grads[c].numpy(), rtol=1e-10, atol=1e-12)
     with pytest.raises(T.NotLowerable):
         T.trace(lambda u, x: F.softplus(u, beta=2.0) + x, 1, None)
+
+
+def test_comparisons_and_where_lower_to_indicators():
+    """ Piecewise coefficients and sources — torch.where(x < 0.5, 1.0, 10.0), (x > 0.2) & (y <= 0.7), ~mask, masks used as
+    numbers — lower to 0 / 1 indicators (1 + sign(.)) / 2: values and partials must match torch's on points off the
+    thresholds.  What stays off the fused path: `if` on a comparison, == / !=, torch.where guarding a branch that may
+    be NaN / inf where it is not selected, boolean algebra on things that are not comparisons. """
+    def eq(u, x, y, D):
+        a = torch.where(x < 0.5, 1.0, 10.0)
+        band = ((x > 0.2) & (y <= 0.7)) | ~(y > 0.1)
+        ring = torch.logical_and(x >= 0.3, torch.logical_not(y < 0.4))
+        return (a * D(u, x) + D(u, y) * torch.where(band, torch.sin(3.0 * x), u * u) + (x > y) * 2.0 + (0.3 < x) * u
+                + torch.where(ring, u, -u * x) - torch.gt(u, 0.1) * y + (u * y).where(x <= 0.6, y ** 2)
+                + torch.where(torch.tensor(True), x, y) + ((x > 0.5) ^ (y > 0.5)) * 0.25)
+    tr = T.trace(lambda u, x, y: eq(u, x, y, T.sym_D), 2, None)
+    assert tr.nf == 2 and tr.ns == 0
+    rng = np.random.RandomState(7)
+    n = 300
+    jet = rng.uniform(-1, 1, size=(3, n))
+    coords = rng.uniform(0, 1, size=(2, n))
+    outs = T.run_program(tr.eq_prog, jet, coords, [])
+    ch = [torch.tensor(jet[c], dtype=torch.float64, requires_grad=True) for c in range(3)]
+    x, y = (torch.tensor(coords[k], dtype=torch.float64) for k in range(2))
+    col = {d: 1 + i for i, d in enumerate(tr.dirs)}
+    r = eq(ch[0], x, y, lambda v, xx: ch[col[0]] if xx is x else ch[col[1]])
+    assert np.allclose(outs[0], r.detach().numpy(), rtol=1e-12, atol=1e-12)
+    grads = torch.autograd.grad(r.sum(), ch)
+    for c in range(3):
+        assert np.allclose(outs[1 + c], grads[c].numpy(), rtol=1e-10, atol=1e-12)
+
+    def raises(f, total=1):
+        with pytest.raises(T.NotLowerable):
+            T.trace(f, total, None)
+    raises(lambda u, x: torch.where(x > 0.5, torch.sqrt(x - 0.5), 0.0 * x) + u)        # guard around a NaN branch
+    raises(lambda u, x: torch.where(x > 0.5, 1.0 / x, x) + u)
+    raises(lambda u, x: torch.where(x > 0.5, torch.exp(x), x) + u)
+    raises(lambda u, x: u if x > 0.5 else -u)                                            # control flow
+    raises(lambda u, x: (x == 0.5) * u)
+    raises(lambda u, x: (x & u))                                                         # not comparisons
+    raises(lambda u, x: torch.where(x, u, -u))
