@@ -474,6 +474,15 @@ class Sym:
     def view(self, *shape): return self
     def reshape(self, *shape): return self
     def float(self): return self
+    def double(self): return self
+    def to(self, *args, **kwargs): return self             # dtype / device casts of a symbolic column are no-ops
+    def type(self, *args, **kwargs): return self
+    def type_as(self, other): return self
+    def clone(self): return self
+    def contiguous(self): return self
+    def squeeze(self, *args): return self
+    def unsqueeze(self, *args): return self
+    dtype = torch.float32
 
     def __bool__(self):
         raise NotLowerable('data-dependent control flow in a traced callable')
