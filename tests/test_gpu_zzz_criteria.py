@@ -97,3 +97,31 @@ def test_constraint_only_fit_stays_on_the_engine_and_matches_autograd(fused_cons
     assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 2e-3
     assert abs(float(fused.model.init.detach()) - float(ref.model.init.detach())) <= 1e-4
     assert float(fused.model.init.detach()) != 3.0
+
+
+def test_piecewise_equation_with_where_trains_fused_like_autograd():
+    """ torch.where / comparisons in the equation (a diffusivity that jumps at x = 0.5, a source switched on in a band)
+    run as indicator arithmetic in the kernel's residual program: the fused fit against the autograd backend executing
+    the user's torch.where, identical weights and batches. """
+    from pydens_b200 import Solver, D
+
+    def pde(u, x, y):
+        a = torch.where(x < 0.5, 1.0, 10.0)
+        return a * D(D(u, x), x) + D(D(u, y), y) - torch.where((x > 0.2) & (y <= 0.7), torch.sin(3.0 * x), torch.zeros_like(x))
+
+    def make(backend):
+        torch.manual_seed(0)
+        return Solver(pde, ndims=2, boundary_condition=0.0, layout='fafaf', features=[10, 8, 1], activation='Tanh',
+                      device='cuda', backend=backend)
+    fused, ref = make('fused'), make('torch')
+    ref.model.load_state_dict(fused.model.state_dict())
+    rng = np.random.RandomState(11)
+    batches = [rng.uniform(0.01, 0.99, size=(128, 2)).astype(np.float32) for _ in range(20)]
+    fused.fit(niters=20, batch_size=128, sampler=Replay(batches), lr=0.01)
+    ref.fit(niters=20, batch_size=128, sampler=Replay(batches), lr=0.01)
+    assert fused._engine is not None
+    a, b = np.asarray(fused.losses, dtype=np.float64), np.asarray(ref.losses, dtype=np.float64)
+    assert a.shape == b.shape == (20,)
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) <= 2e-3
+    grid = np.linspace(0.05, 0.95, 9)
+    assert np.abs(fused.predict(grid, 0.5) - ref.predict(grid, 0.5)).max() <= 1e-4
