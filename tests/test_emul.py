@@ -234,3 +234,35 @@ def test_emulated_fit_with_other_criteria_follows_the_reference_loop(key, make):
     losses, want = np.asarray(losses, dtype=np.float64), prob.flat_params().numpy()
     assert np.max(np.abs(losses - ref) / np.maximum(np.abs(ref), 1e-6)) <= 2e-4
     assert np.linalg.norm(params[:want.size] - want) / np.linalg.norm(want) <= 2e-4
+
+
+@pytest.mark.parametrize('key,make', [(('l1',), lambda: torch.nn.L1Loss()), (('huber', 0.2), lambda: torch.nn.HuberLoss(delta=0.2)),
+                                      (('smooth_l1', 0.15), lambda: torch.nn.SmoothL1Loss(beta=0.15))], ids=['l1', 'huber', 'smooth_l1'])
+def test_constraint_plans_follow_the_criterion(key, make):
+    """ reference :457 `criterion(constraint(...), [0.])`: a lowered constraint is trained with the criterion of the fit,
+    like the equation term — value and gradients against torch's criterion on the fp64 oracle. """
+    from pydens_b200 import tracer as T, _native as N
+    name = 'heat1d_icvar'
+    cfg = P.PROBLEMS[name]
+    g = load_golden(name)
+    main, main_tr = E.spec_for(name), E.traced_problem(name)
+    sym_V = lambda n, init: T.Sym(T.var(n))
+    xs0, ts0 = torch.tensor([0.25, 0.5, 0.8, 0.1, 0.65]), torch.tensor([0.3, 0.6, 0.05, 0.9, 0.4])
+
+    def constraint(u, x, t, V=sym_V):
+        return u(xs0, ts0) ** 2 - 0.3 * V('shift', 0.2)
+    tr, _ = T.trace_constraint(constraint, 2, initial_condition=P.make_ic(name, sym_V), ndims_spatial=1, criterion=key)
+    var_offsets = {n: main.var_off[i] for i, n in enumerate(main_tr.var_names)}
+    acts, skips = P.layer_plan(name)
+    spec = N.build_spec([2] + list(cfg['features']), acts, 2, 0, True, cfg['bc'], True, [(0, 1), (0, 1)], tr,
+                        var_offsets=var_offsets, w_off=list(main.w_off[:3]), b_off=list(main.b_off[:3]),
+                        log_scale_off=main.log_scale_off, n_params=main.n_params, skips=skips)
+    pts = torch.stack([xs0, ts0], dim=1).numpy()
+    loss, _, grads = E.emul_step(spec, g['params'], pts)
+    prob = oracle_problem(name, torch.float64, g['params'].astype(np.float64))
+    prob.equation = lambda u, x, t, D, V: u ** 2 - 0.3 * V('shift')
+    ref_loss, ref_res, ref_grads = prob.loss_and_grads(pts.astype(np.float64), criterion=make())
+    if key[0] != 'l1':
+        assert (np.abs(ref_res) < key[1]).any() and (np.abs(ref_res) > key[1]).any()
+    assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert rel_l2(grads[:ref_grads.numel()], ref_grads.numpy()) <= 2e-5
