@@ -592,6 +592,10 @@ class Sym:
             return Sym(_REWRITES2[name](_as_expr(args[0]), _as_expr(args[1])))
         if name == 'where' and len(args) == 3:
             return Sym(_where(args[0], args[1], args[2]))
+        if name == 'heaviside' and len(args) == 2:
+            # 0 below, `values` at, 1 above zero:  (1 + s) / 2 + (values - 1/2) (1 - s^2)  with s = sign(input)
+            sg, v = unary('sign', _as_expr(args[0])), _as_expr(args[1])
+            return Sym(add(mul(const(0.5), add(ONE, sg)), mul(sub(v, const(0.5)), sub(ONE, mul(sg, sg)))))
         if name in ('gt', 'ge', 'lt', 'le', 'greater', 'greater_equal', 'less', 'less_equal') and len(args) == 2:
             flip = name in ('lt', 'le', 'less', 'less_equal')
             if isinstance(args[0], Sym):
