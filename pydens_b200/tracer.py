@@ -350,7 +350,7 @@ def _as_expr(x):
 
 _TORCH_UNARY = {'sin': 'sin', 'cos': 'cos', 'tan': 'tan', 'exp': 'exp', 'log': 'log', 'sqrt': 'sqrt',
                 'tanh': 'tanh', 'sigmoid': 'sigmoid', 'abs': 'abs', 'absolute': 'abs', 'neg': 'neg',
-                'negative': 'neg', 'sign': 'sign'}
+                'negative': 'neg', 'sign': 'sign', 'sgn': 'sign'}
 _TORCH_BINARY = {'add': add, 'sub': sub, 'subtract': sub, 'mul': mul, 'multiply': mul, 'div': div,
                  'divide': div, 'true_divide': div, 'pow': power}
 _NP_UNARY = {np.sin: 'sin', np.cos: 'cos', np.tan: 'tan', np.exp: 'exp', np.log: 'log', np.sqrt: 'sqrt',
@@ -370,6 +370,8 @@ _REWRITES = {
     'log10': lambda a: mul(const(1.0 / math.log(10.0)), unary('log', a)),
     # piecewise-linear functions through |.|: exact where they are linear, torch's values everywhere, torch's
     # derivatives except exactly at the kink (there: the mean of the one-sided ones)
+    'expm1': lambda a: mul(unary('tanh', mul(const(0.5), a)), add(unary('exp', a), ONE)),   # e^a - 1 = tanh(a / 2) (e^a + 1): no cancellation near 0
+    'log1p': lambda a: unary('log', add(ONE, a)),        # absolute error of one rounding of 1 + a (1e-7 in fp32), not a relative one
     'relu': lambda a: mul(const(0.5), add(a, unary('abs', a))),
     'silu': lambda a: mul(a, unary('sigmoid', a)),
     'softplus': lambda a: add(mul(const(0.5), add(a, unary('abs', a))),                     # max(a, 0) + log(1 + e^-|a|)
